@@ -1,0 +1,306 @@
+// sp_device.cuh — device building blocks of the B200 spectrogram engine (sm_100a).
+//
+//  * sample decoders: bit-exact fp32 versions of SampleView.sampleI/Q
+//    (reference lib/samples.js:313-400), i.e. gpu == fround(reference double)
+//  * register-resident radix-2/4/8/16 butterflies used by the shared-memory FFT
+//    (replaces the radix-2 transform of reference lib/fft_nayuki.js:54-86)
+//  * JS number helpers (`~~v`)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sp {
+
+enum Format : int {
+    CU4 = 0, CS4, CU8, CS8, CU12, CS12, CU16, CS16, CU32, CS32, CU64, CS64, CF32, CF64, FORMAT_COUNT,
+    FMT_RUNTIME = -1   // decode through a runtime switch on the format
+};
+
+__host__ __device__ constexpr int sample_width(int f)
+{
+    return (f == CU4 || f == CS4) ? 1 : (f == CU8 || f == CS8) ? 2 : (f == CU12 || f == CS12) ? 3
+         : (f == CU16 || f == CS16) ? 4 : (f == CU32 || f == CS32 || f == CF32) ? 8 : 16;
+}
+__host__ __device__ constexpr int element_size(int f)
+{
+    return (f <= CS12) ? 1 : (f == CU16 || f == CS16) ? 2 : (f == CF64) ? 8 : 4;
+}
+
+// ------------------------------------------------------------------ JS helpers
+
+// `~~v` for a float: truncate toward zero; NaN, +-Inf and anything outside int32 give 0
+// (the reference wraps modulo 2^32 out there; those magnitudes do not occur on this path).
+__device__ __forceinline__ int js_trunc(float v)
+{
+    int r = __float2int_rz(v);              // NaN -> 0, saturating
+    return (fabsf(v) < 2147483648.0f) ? r : 0;
+}
+
+// ------------------------------------------------------------------ conversions (raw code -> fp32)
+// Each matches fround() of the reference's double expression for EVERY code (SURVEY A.1;
+// the three non-power-of-two biases need a correctly rounded IEEE division).
+
+__device__ __forceinline__ float cv_u4(int c) { return __fdiv_rn((float)(2 * c - 15), 15.0f); }       // (c-7.5)*(1/7.5)
+__device__ __forceinline__ float cv_s4(int c) { return (float)c * 0.125f; }                           // c*(1/8)
+__device__ __forceinline__ float cv_u8(int c) { return __fdiv_rn((float)(2 * c - 255), 255.0f); }     // (c-127.5)*(1/127.5)
+__device__ __forceinline__ float cv_s8(int c) { return (float)c * 0.0078125f; }                       // c*(1/128)
+__device__ __forceinline__ float cv_u12(int c) { return __fdiv_rn((float)(2 * c - 4095), 4095.0f); }  // (c-2047.5)*(1/2047.5)
+__device__ __forceinline__ float cv_s12(int c) { return (float)c * 0.00048828125f; }                  // c*(1/2048)
+__device__ __forceinline__ float cv_u16(int c) { return (float)(2 * c - 65535) * 1.52587890625e-05f; }// (c-32767.5)/32768, exact
+__device__ __forceinline__ float cv_s16(int c) { return (float)c * 3.0517578125e-05f; }               // c/32768, exact
+__device__ __forceinline__ float cv_u32(uint32_t c)
+{   // (c - 2147483647.5) / 2^31 : exact 33-bit integer, one rounding
+    return __ll2float_rn(2ll * (long long)c - 4294967295ll) * 2.3283064365386963e-10f;
+}
+__device__ __forceinline__ float cv_s32(uint32_t c) { return __int2float_rn((int)c) * 4.656612873077393e-10f; }
+__device__ __forceinline__ float cv_u64(uint32_t lo, uint32_t hi)
+{   // hi/2^31 + lo/2^64 - 1   (lib/samples.js:368-369; both quotients exact, two roundings like JS)
+    double s = __dadd_rn((double)hi * 4.656612873077393e-10, (double)lo * 5.421010862427522e-20);
+    return __double2float_rn(__dadd_rn(s, -1.0));
+}
+__device__ __forceinline__ float cv_s64(uint32_t lo, uint32_t hi)
+{   // (hi>>0)/2^31 + lo/2^64   (lib/samples.js:382)
+    return __double2float_rn(__dadd_rn((double)(int)hi * 4.656612873077393e-10, (double)lo * 5.421010862427522e-20));
+}
+
+__device__ __forceinline__ int sext(int v, int bits) { return (v << (32 - bits)) >> (32 - bits); }
+
+// ------------------------------------------------------------------ fast (in-range) decode of sample s
+// `buf` must be 16-byte aligned at sample 0; returns (I, Q).
+template <int FMT>
+__device__ __forceinline__ float2 decode_fast(const uint8_t *__restrict__ buf, long long s, int rt_fmt)
+{
+    if constexpr (FMT == FMT_RUNTIME) {
+        switch (rt_fmt) {
+        case CU4: return decode_fast<CU4>(buf, s, 0);
+        case CS4: return decode_fast<CS4>(buf, s, 0);
+        case CU8: return decode_fast<CU8>(buf, s, 0);
+        case CS8: return decode_fast<CS8>(buf, s, 0);
+        case CU12: return decode_fast<CU12>(buf, s, 0);
+        case CS12: return decode_fast<CS12>(buf, s, 0);
+        case CU16: return decode_fast<CU16>(buf, s, 0);
+        case CS16: return decode_fast<CS16>(buf, s, 0);
+        case CU32: return decode_fast<CU32>(buf, s, 0);
+        case CS32: return decode_fast<CS32>(buf, s, 0);
+        case CU64: return decode_fast<CU64>(buf, s, 0);
+        case CS64: return decode_fast<CS64>(buf, s, 0);
+        case CF32: return decode_fast<CF32>(buf, s, 0);
+        default: return decode_fast<CF64>(buf, s, 0);
+        }
+    } else if constexpr (FMT == CU4) {
+        int b = buf[s];
+        return make_float2(cv_u4(b >> 4), cv_u4(b & 15));
+    } else if constexpr (FMT == CS4) {
+        int b = buf[s];
+        return make_float2(cv_s4(sext(b >> 4, 4)), cv_s4(sext(b & 15, 4)));
+    } else if constexpr (FMT == CU8) {
+        unsigned v = *reinterpret_cast<const unsigned short *>(buf + 2 * s);
+        return make_float2(cv_u8(v & 255), cv_u8(v >> 8));
+    } else if constexpr (FMT == CS8) {
+        unsigned v = *reinterpret_cast<const unsigned short *>(buf + 2 * s);
+        return make_float2(cv_s8((int)(signed char)(v & 255)), cv_s8((int)(signed char)(v >> 8)));
+    } else if constexpr (FMT == CU12 || FMT == CS12) {
+        const uint8_t *p = buf + 3 * s;
+        int b0 = p[0], b1 = p[1], b2 = p[2];
+        int i = ((b1 & 15) << 8) | b0, q = (b2 << 4) | (b1 >> 4);     // lib/samples.js:340,346
+        if constexpr (FMT == CU12) return make_float2(cv_u12(i), cv_u12(q));
+        return make_float2(cv_s12(sext(i, 12)), cv_s12(sext(q, 12)));
+    } else if constexpr (FMT == CU16) {
+        unsigned v = *reinterpret_cast<const unsigned *>(buf + 4 * s);
+        return make_float2(cv_u16(v & 0xffff), cv_u16(v >> 16));
+    } else if constexpr (FMT == CS16) {
+        unsigned v = *reinterpret_cast<const unsigned *>(buf + 4 * s);
+        return make_float2(cv_s16((int)(short)(v & 0xffff)), cv_s16((int)v >> 16));
+    } else if constexpr (FMT == CU32) {
+        uint2 v = *reinterpret_cast<const uint2 *>(buf + 8 * s);
+        return make_float2(cv_u32(v.x), cv_u32(v.y));
+    } else if constexpr (FMT == CS32) {
+        uint2 v = *reinterpret_cast<const uint2 *>(buf + 8 * s);
+        return make_float2(cv_s32(v.x), cv_s32(v.y));
+    } else if constexpr (FMT == CU64) {
+        uint4 v = *reinterpret_cast<const uint4 *>(buf + 16 * s);
+        return make_float2(cv_u64(v.x, v.y), cv_u64(v.z, v.w));
+    } else if constexpr (FMT == CS64) {
+        uint4 v = *reinterpret_cast<const uint4 *>(buf + 16 * s);
+        return make_float2(cv_s64(v.x, v.y), cv_s64(v.z, v.w));
+    } else if constexpr (FMT == CF32) {
+        return *reinterpret_cast<const float2 *>(buf + 8 * s);
+    } else {
+        double2 v = *reinterpret_cast<const double2 *>(buf + 16 * s);
+        return make_float2(__double2float_rn(v.x), __double2float_rn(v.y));
+    }
+}
+
+// ------------------------------------------------------------------ bounds-checked decode
+// Reference semantics for reads outside the typed array (`undefined`): NaN for the plain
+// formats, 0-bits for the packed nibble / 12-bit formats, and for CS64 a missing high word
+// is `undefined >> 0 == 0`.  Slow path: only frames that touch the end of a ragged buffer.
+__device__ __forceinline__ uint32_t rd_bytes(const uint8_t *buf, long long off, int nb, unsigned long long valid, bool &ok)
+{
+    ok = off >= 0 && (unsigned long long)(off + nb) <= valid;
+    uint32_t v = 0;
+    if (ok) for (int i = 0; i < nb; i++) v |= (uint32_t)buf[off + i] << (8 * i);
+    return v;
+}
+
+static __device__ __noinline__ float2 decode_checked(const uint8_t *__restrict__ buf, long long s, int fmt,
+                                              unsigned long long valid_bytes)
+{
+    const float qnan = __int_as_float(0x7fc00000);
+    // typed-array length in whole elements
+    const unsigned long long valid = valid_bytes - valid_bytes % (unsigned)element_size(fmt);
+    bool ok0, ok1, ok2, ok3;
+    float2 r;
+    switch (fmt) {
+    case CU4: case CS4: {
+        int b = (int)rd_bytes(buf, s, 1, valid, ok0);
+        if (fmt == CU4) return make_float2(cv_u4(b >> 4), cv_u4(b & 15));
+        return make_float2(cv_s4(sext(b >> 4, 4)), cv_s4(sext(b & 15, 4)));
+    }
+    case CU12: case CS12: {
+        int b0 = (int)rd_bytes(buf, 3 * s, 1, valid, ok0);
+        int b1 = (int)rd_bytes(buf, 3 * s + 1, 1, valid, ok1);
+        int b2 = (int)rd_bytes(buf, 3 * s + 2, 1, valid, ok2);
+        int i = ((b1 & 15) << 8) | b0, q = (b2 << 4) | (b1 >> 4);
+        if (fmt == CU12) return make_float2(cv_u12(i), cv_u12(q));
+        return make_float2(cv_s12(sext(i, 12)), cv_s12(sext(q, 12)));
+    }
+    case CU8: case CS8: {
+        int a = (int)rd_bytes(buf, 2 * s, 1, valid, ok0), b = (int)rd_bytes(buf, 2 * s + 1, 1, valid, ok1);
+        r = (fmt == CU8) ? make_float2(cv_u8(a), cv_u8(b)) : make_float2(cv_s8((signed char)a), cv_s8((signed char)b));
+        break;
+    }
+    case CU16: case CS16: {
+        int a = (int)rd_bytes(buf, 4 * s, 2, valid, ok0), b = (int)rd_bytes(buf, 4 * s + 2, 2, valid, ok1);
+        r = (fmt == CU16) ? make_float2(cv_u16(a), cv_u16(b)) : make_float2(cv_s16((short)a), cv_s16((short)b));
+        break;
+    }
+    case CU32: case CS32: case CF32: {
+        uint32_t a = rd_bytes(buf, 8 * s, 4, valid, ok0), b = rd_bytes(buf, 8 * s + 4, 4, valid, ok1);
+        r = (fmt == CU32) ? make_float2(cv_u32(a), cv_u32(b))
+          : (fmt == CS32) ? make_float2(cv_s32(a), cv_s32(b))
+                          : make_float2(__uint_as_float(a), __uint_as_float(b));
+        break;
+    }
+    case CU64: case CS64: {
+        uint32_t l0 = rd_bytes(buf, 16 * s, 4, valid, ok0), h0 = rd_bytes(buf, 16 * s + 4, 4, valid, ok1);
+        uint32_t l1 = rd_bytes(buf, 16 * s + 8, 4, valid, ok2), h1 = rd_bytes(buf, 16 * s + 12, 4, valid, ok3);
+        if (fmt == CU64) {
+            r = make_float2(cv_u64(l0, h0), cv_u64(l1, h1));
+            ok0 = ok0 && ok1; ok1 = ok2 && ok3;
+        } else {
+            r = make_float2(cv_s64(l0, h0), cv_s64(l1, h1));   // missing hi word reads as 0
+            ok1 = ok2;
+        }
+        break;
+    }
+    default: { // CF64
+        uint32_t a0 = rd_bytes(buf, 16 * s, 4, valid, ok0), a1 = rd_bytes(buf, 16 * s + 4, 4, valid, ok2);
+        uint32_t b0 = rd_bytes(buf, 16 * s + 8, 4, valid, ok1), b1 = rd_bytes(buf, 16 * s + 12, 4, valid, ok3);
+        ok0 = ok0 && ok2; ok1 = ok1 && ok3;
+        r = make_float2(__double2float_rn(__hiloint2double((int)a1, (int)a0)),
+                        __double2float_rn(__hiloint2double((int)b1, (int)b0)));
+        break;
+    }
+    }
+    if (!ok0) r.x = qnan;
+    if (!ok1) r.y = qnan;
+    return r;
+}
+
+// ------------------------------------------------------------------ complex helpers
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 w)
+{
+    return make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
+}
+// multiply by -j  (W4^1 of the forward transform)
+__device__ __forceinline__ float2 mul_mj(float2 a) { return make_float2(a.y, -a.x); }
+
+// forward DFT-2 / DFT-4 on registers: y[k] = sum_n x[n] * exp(-2 pi j n k / R)
+__device__ __forceinline__ void dft2(float2 &a, float2 &b)
+{
+    float2 t = a; a = cadd(t, b); b = csub(t, b);
+}
+__device__ __forceinline__ void dft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3)
+{
+    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_mj(csub(a1, a3));
+    a0 = cadd(t0, t2); a2 = csub(t0, t2);
+    a1 = cadd(t1, t3); a3 = csub(t1, t3);
+}
+
+#define SP_SQRT1_2 0.70710678118654752440f
+#define SP_COS_PI_8 0.92387953251128675613f
+#define SP_SIN_PI_8 0.38268343236508977173f
+
+// in place, natural order in -> natural order out
+template <int R> __device__ __forceinline__ void dft(float2 (&v)[R]);
+
+template <> __device__ __forceinline__ void dft<1>(float2 (&)[1]) {}
+template <> __device__ __forceinline__ void dft<2>(float2 (&v)[2]) { dft2(v[0], v[1]); }
+template <> __device__ __forceinline__ void dft<4>(float2 (&v)[4]) { dft4(v[0], v[1], v[2], v[3]); }
+
+template <> __device__ __forceinline__ void dft<8>(float2 (&v)[8])
+{
+    // n = 4*n1 + n0, k = k0 + 2*k1 :  W8^{nk} = W2^{n1 k0} * W8^{n0 k0} * W4^{n0 k1}
+#pragma unroll
+    for (int n0 = 0; n0 < 4; n0++) dft2(v[n0], v[4 + n0]);       // v[n0] : k0 = 0, v[4+n0] : k0 = 1
+    // k0 = 1 row times W8^{n0}
+    {
+        float2 a = v[5]; v[5] = make_float2(SP_SQRT1_2 * (a.x + a.y), SP_SQRT1_2 * (a.y - a.x));   // W8^1
+        v[6] = mul_mj(v[6]);                                                                        // W8^2
+        a = v[7]; v[7] = make_float2(SP_SQRT1_2 * (a.y - a.x), -SP_SQRT1_2 * (a.x + a.y));         // W8^3
+    }
+    dft4(v[0], v[1], v[2], v[3]);   // k0 = 0 : outputs k = 0,2,4,6
+    dft4(v[4], v[5], v[6], v[7]);   // k0 = 1 : outputs k = 1,3,5,7
+    float2 y[8];
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++) { y[2 * k1] = v[k1]; y[2 * k1 + 1] = v[4 + k1]; }
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = y[i];
+}
+
+template <> __device__ __forceinline__ void dft<16>(float2 (&v)[16])
+{
+    // n = 4*n1 + n0, k = k0 + 4*k1 :  W16^{nk} = W4^{n1 k0} * W16^{n0 k0} * W4^{n0 k1}
+#pragma unroll
+    for (int n0 = 0; n0 < 4; n0++) dft4(v[n0], v[4 + n0], v[8 + n0], v[12 + n0]);   // v[4*k0 + n0]
+    // twiddles W16^{n0*k0}
+    {
+        const float C = SP_COS_PI_8, S = SP_SIN_PI_8, H = SP_SQRT1_2;
+        float2 a;
+        v[5] = cmul(v[5], make_float2(C, -S));                                  // k0=1,n0=1 : W16^1
+        a = v[6]; v[6] = make_float2(H * (a.x + a.y), H * (a.y - a.x));         // k0=1,n0=2 : W16^2
+        v[7] = cmul(v[7], make_float2(S, -C));                                  // k0=1,n0=3 : W16^3
+        a = v[9]; v[9] = make_float2(H * (a.x + a.y), H * (a.y - a.x));         // k0=2,n0=1 : W16^2
+        v[10] = mul_mj(v[10]);                                                  // k0=2,n0=2 : W16^4
+        a = v[11]; v[11] = make_float2(H * (a.y - a.x), -H * (a.x + a.y));      // k0=2,n0=3 : W16^6
+        v[13] = cmul(v[13], make_float2(S, -C));                                // k0=3,n0=1 : W16^3
+        a = v[14]; v[14] = make_float2(H * (a.y - a.x), -H * (a.x + a.y));      // k0=3,n0=2 : W16^6
+        v[15] = cmul(v[15], make_float2(-C, S));                                // k0=3,n0=3 : W16^9
+    }
+#pragma unroll
+    for (int k0 = 0; k0 < 4; k0++) dft4(v[4 * k0], v[4 * k0 + 1], v[4 * k0 + 2], v[4 * k0 + 3]);  // -> k1
+    float2 y[16];
+#pragma unroll
+    for (int k0 = 0; k0 < 4; k0++)
+#pragma unroll
+        for (int k1 = 0; k1 < 4; k1++) y[k0 + 4 * k1] = v[4 * k0 + k1];
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = y[i];
+}
+
+// v[k] *= w^k for k = 1..15, given w^1, w^2, w^4, w^8 (11 complex products, depth <= 3)
+__device__ __forceinline__ void twiddle16(float2 (&v)[16], float2 w1, float2 w2, float2 w4, float2 w8)
+{
+    float2 w3 = cmul(w1, w2), w5 = cmul(w1, w4), w6 = cmul(w2, w4), w7 = cmul(w3, w4);
+    v[1] = cmul(v[1], w1);  v[2] = cmul(v[2], w2);  v[3] = cmul(v[3], w3);  v[4] = cmul(v[4], w4);
+    v[5] = cmul(v[5], w5);  v[6] = cmul(v[6], w6);  v[7] = cmul(v[7], w7);  v[8] = cmul(v[8], w8);
+    v[9] = cmul(v[9], cmul(w1, w8));   v[10] = cmul(v[10], cmul(w2, w8)); v[11] = cmul(v[11], cmul(w3, w8));
+    v[12] = cmul(v[12], cmul(w4, w8)); v[13] = cmul(v[13], cmul(w5, w8)); v[14] = cmul(v[14], cmul(w6, w8));
+    v[15] = cmul(v[15], cmul(w7, w8));
+}
+
+} // namespace sp

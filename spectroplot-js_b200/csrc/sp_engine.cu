@@ -1,0 +1,627 @@
+// sp_engine.cu — host side of the C ABI declared in include/spectro_b200.h.
+//
+// Re-hosts what the reference worker does around its hot loops (lib/worker.js:23-62,
+// 140-155): argument unpacking, derived constants, output allocation, and the reply.
+// No CPU fallback exists: without an sm_100 device sp_create fails with SP_E_NO_DEVICE.
+#include "../../include/spectro_b200.h"
+#include "sp_aux_kernels.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <strings.h>
+#include <vector>
+
+using sp::Params;
+
+// ---- per-format kernel entry points (weak: a build may carry any subset, "rt" is mandatory) ----
+#define SP_DECL(tag)                                                                                             \
+    extern "C" cudaError_t sp_rl_##tag(int, const Params *, int, size_t, cudaStream_t, int *) __attribute__((weak)); \
+    extern "C" cudaError_t sp_pl_##tag(int, const Params *, float2 *, const float2 *, cudaStream_t) __attribute__((weak));
+SP_DECL(rt) SP_DECL(cu4) SP_DECL(cs4) SP_DECL(cu8) SP_DECL(cs8) SP_DECL(cu12) SP_DECL(cs12) SP_DECL(cu16)
+SP_DECL(cs16) SP_DECL(cu32) SP_DECL(cs32) SP_DECL(cu64) SP_DECL(cs64) SP_DECL(cf32) SP_DECL(cf64)
+
+typedef cudaError_t (*render_fn)(int, const Params *, int, size_t, cudaStream_t, int *);
+typedef cudaError_t (*prepass_fn)(int, const Params *, float2 *, const float2 *, cudaStream_t);
+
+static render_fn render_for(int fmt)
+{
+    static const render_fn tab[SP_FORMAT_COUNT] = { sp_rl_cu4, sp_rl_cs4, sp_rl_cu8, sp_rl_cs8, sp_rl_cu12, sp_rl_cs12,
+        sp_rl_cu16, sp_rl_cs16, sp_rl_cu32, sp_rl_cs32, sp_rl_cu64, sp_rl_cs64, sp_rl_cf32, sp_rl_cf64 };
+    return tab[fmt] ? tab[fmt] : sp_rl_rt;
+}
+static prepass_fn prepass_for(int fmt)
+{
+    static const prepass_fn tab[SP_FORMAT_COUNT] = { sp_pl_cu4, sp_pl_cs4, sp_pl_cu8, sp_pl_cs8, sp_pl_cu12, sp_pl_cs12,
+        sp_pl_cu16, sp_pl_cs16, sp_pl_cu32, sp_pl_cs32, sp_pl_cu64, sp_pl_cs64, sp_pl_cf32, sp_pl_cf64 };
+    return tab[fmt] ? tab[fmt] : sp_pl_rt;
+}
+static bool specialised(int fmt)
+{
+    static const render_fn tab[SP_FORMAT_COUNT] = { sp_rl_cu4, sp_rl_cs4, sp_rl_cu8, sp_rl_cs8, sp_rl_cu12, sp_rl_cs12,
+        sp_rl_cu16, sp_rl_cs16, sp_rl_cu32, sp_rl_cs32, sp_rl_cu64, sp_rl_cs64, sp_rl_cf32, sp_rl_cf64 };
+    return tab[fmt] != nullptr;
+}
+
+// ------------------------------------------------------------------ formats (lib/samples.js:22-155)
+static const char *const k_names[SP_FORMAT_COUNT] = { "CU4", "CS4", "CU8", "CS8", "CU12", "CS12", "CU16", "CS16",
+                                                       "CU32", "CS32", "CU64", "CS64", "CF32", "CF64" };
+
+extern "C" int sp_abi_version(void) { return SP_ABI_VERSION; }
+
+extern "C" int sp_format_from_name(const char *name)
+{
+    if (!name) return SP_CU8;
+    for (int i = 0; i < SP_FORMAT_COUNT; i++)
+        if (!strcasecmp(name, k_names[i])) return i;
+    if (!strcasecmp(name, "DATA") || !strcasecmp(name, "COMPLEX16U")) return SP_CU8;
+    if (!strcasecmp(name, "COMPLEX16S")) return SP_CS8;
+    if (!strcasecmp(name, "CFILE") || !strcasecmp(name, "COMPLEX")) return SP_CF32;
+    return SP_CU8;   // lib/samples.js:149-155: anything else is treated as CU8
+}
+extern "C" const char *sp_format_name(int f) { return (f < 0 || f >= SP_FORMAT_COUNT) ? "?" : k_names[f]; }
+extern "C" int sp_sample_width(int f) { return (f < 0 || f >= SP_FORMAT_COUNT) ? SP_E_BAD_FORMAT : sp::sample_width(f); }
+extern "C" int sp_element_size(int f) { return (f < 0 || f >= SP_FORMAT_COUNT) ? SP_E_BAD_FORMAT : sp::element_size(f); }
+
+// ------------------------------------------------------------------ engine state
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct sp_engine {
+    int ndev = 1;
+    int dev = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    std::string plan;
+    std::map<int, float2 *> tw;              // twiddle tables by n
+    DevBuf in, image, fmin, fmax, fmid, gauges, hist, stats, lut, window, scratch, db, synth_lut;
+    // state of an enqueued (not yet finished) render
+    bool pending = false;
+    long long pend_width = 0;
+    int pend_cmap_len = 0;
+    int launches = 0;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(sp_engine *e, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (e) e->err = buf; else g_create_err = buf;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _c = (call);                                                                   \
+        if (_c != cudaSuccess) return fail(e, SP_E_CUDA, "%s: %s", #call, cudaGetErrorString(_c)); \
+    } while (0)
+
+static int ensure(sp_engine *e, DevBuf &b, size_t bytes)
+{
+    if (b.cap >= bytes && b.p) return SP_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = (bytes + 255) & ~(size_t)255;
+    if (want == 0) want = 256;
+    cudaError_t c = cudaMalloc(&b.p, want);
+    if (c != cudaSuccess) { b.p = nullptr; return fail(e, SP_E_CUDA, "cudaMalloc(%zu): %s", want, cudaGetErrorString(c)); }
+    b.cap = want;
+    return SP_OK;
+}
+
+extern "C" const char *sp_last_error(sp_engine *e) { return e ? e->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int sp_create(sp_engine **out, const int *device_ids, int ndev)
+{
+    if (!out) return fail(nullptr, SP_E_INVAL, "sp_create: out is null");
+    *out = nullptr;
+    if (ndev < 1) ndev = 1;
+    if (ndev > 1) return fail(nullptr, SP_E_INVAL, "sp_create: one device per engine in this build; shard with sp_request.frame_first / total_width (one engine per GPU)");
+    int count = 0;
+    cudaError_t c = cudaGetDeviceCount(&count);
+    if (c != cudaSuccess || count == 0)
+        return fail(nullptr, SP_E_NO_DEVICE, "no CUDA device (%s); this engine has no CPU fallback",
+                    c != cudaSuccess ? cudaGetErrorString(c) : "device count is 0");
+    const int dev = device_ids ? device_ids[0] : 0;
+    if (dev < 0 || dev >= count) return fail(nullptr, SP_E_NO_DEVICE, "device %d out of range (count %d)", dev, count);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return fail(nullptr, SP_E_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail(nullptr, SP_E_NO_DEVICE, "device %d is sm_%d%d; kernels are built for sm_100a only (no fallback)", dev,
+                    prop.major, prop.minor);
+    sp_engine *e = new sp_engine();
+    e->dev = dev;
+    e->sm_count = prop.multiProcessorCount;
+    if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess) {
+        int rc = fail(nullptr, SP_E_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete e;
+        return rc;
+    }
+    e->stream = e->own_stream;
+    *out = e;
+    return SP_OK;
+}
+
+extern "C" void sp_destroy(sp_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->dev);
+    cudaDeviceSynchronize();
+    for (auto &kv : e->tw) cudaFree(kv.second);
+    DevBuf *bufs[] = { &e->in, &e->image, &e->fmin, &e->fmax, &e->fmid, &e->gauges, &e->hist, &e->stats,
+                       &e->lut, &e->window, &e->scratch, &e->db, &e->synth_lut };
+    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+extern "C" int sp_set_stream(sp_engine *e, void *cuda_stream)
+{
+    if (!e) return SP_E_INVAL;
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return SP_OK;
+}
+extern "C" int sp_device_count(sp_engine *e) { return e ? e->ndev : 0; }
+extern "C" int sp_sm_count(sp_engine *e) { return e ? e->sm_count : 0; }
+
+// ------------------------------------------------------------------ helpers
+static int ilog2_exact(int n)
+{
+    for (int i = 0; i < 31; i++) if ((1 << i) == n) return i;
+    return -1;
+}
+
+static int get_twiddles(sp_engine *e, int n, const float2 **out)
+{
+    auto it = e->tw.find(n);
+    if (it != e->tw.end()) { *out = it->second; return SP_OK; }
+    std::vector<float2> h((size_t)n);
+    for (int i = 0; i < n; i++) {                      // computed in double, rounded once
+        const double a = 2.0 * M_PI * (double)i / (double)n;
+        h[i] = make_float2((float)cos(a), (float)-sin(a));
+    }
+    float2 *d = nullptr;
+    CU(cudaMalloc(&d, sizeof(float2) * (size_t)n));
+    CU(cudaMemcpyAsync(d, h.data(), sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->tw[n] = d;
+    *out = d;
+    return SP_OK;
+}
+
+struct Plan {
+    int log2k = 0;       // kernel FFT size (log2)
+    int sub_r = 1;       // pre-pass radix (n = sub_r * 4096 when > 1)
+    int tile = 0;        // frames per CTA tile
+    int smem_x = 0;      // exchange area in float2
+};
+
+template <int L> static void fill_cfg(Plan &pl)
+{
+    pl.tile = sp::Cfg<L>::TILE;
+    pl.smem_x = sp::Cfg<L>::SMEM_X;
+}
+static Plan make_plan(int log2n)
+{
+    Plan pl;
+    if (log2n > 12) { pl.log2k = 12; pl.sub_r = 1 << (log2n - 12); } else pl.log2k = log2n;
+    switch (pl.log2k) {
+    case 3: fill_cfg<3>(pl); break;   case 4: fill_cfg<4>(pl); break;   case 5: fill_cfg<5>(pl); break;
+    case 6: fill_cfg<6>(pl); break;   case 7: fill_cfg<7>(pl); break;   case 8: fill_cfg<8>(pl); break;
+    case 9: fill_cfg<9>(pl); break;   case 10: fill_cfg<10>(pl); break; case 11: fill_cfg<11>(pl); break;
+    default: fill_cfg<12>(pl); break;
+    }
+    if (pl.sub_r > 1) pl.tile = 8;    // sub-frame tiles: 8 frames x one sub-sequence
+    return pl;
+}
+
+extern "C" const char *sp_kernel_plan(sp_engine *e, int format, int n, int channel_mode)
+{
+    if (!e) return "";
+    const int l = ilog2_exact(n);
+    char buf[256];
+    if (l < 3 || l > 16 || format < 0 || format >= SP_FORMAT_COUNT) { e->plan = "unsupported"; return e->plan.c_str(); }
+    Plan pl = make_plan(l);
+    snprintf(buf, sizeof buf, "%s%srender_kernel<N=%d,%s> tile=%d frames smem_x=%d B%s", pl.sub_r > 1 ? "prepass_kernel<R=" : "",
+             pl.sub_r > 1 ? (std::to_string(pl.sub_r) + "> + ").c_str() : "", 1 << pl.log2k,
+             specialised(format) ? k_names[format] : "runtime-format", pl.tile, pl.smem_x * 8, channel_mode ? " +splitreal" : "");
+    e->plan = buf;
+    return e->plan.c_str();
+}
+
+// Everything a render needs on the device, resolved from a request.
+struct Job {
+    Params p;
+    Plan plan;
+    int log2n = 0;
+    long long width = 0;       // local frames
+    double range = 0, gain = 0;
+    uint8_t *d_image = nullptr;
+    uint8_t *d_gmin = nullptr, *d_gmax = nullptr, *d_gamp = nullptr;
+    unsigned long long *d_cb = nullptr, *d_c = nullptr;
+    double *d_stats = nullptr;
+};
+
+static int validate(sp_engine *e, const sp_request *rq, bool shard, double *sample_count, double *stride)
+{
+    if (!rq->buffer || !rq->windowc || !rq->cmap_rgb) return fail(e, SP_E_INVAL, "buffer, windowc and cmap_rgb are required");
+    if (rq->format < 0 || rq->format >= SP_FORMAT_COUNT) return fail(e, SP_E_BAD_FORMAT, "format %d out of range", rq->format);
+    const int l = ilog2_exact(rq->n);
+    if (l < 0) return fail(e, SP_E_BAD_N, "Length is not a power of 2");          // lib/fft_nayuki.js:39
+    if (rq->n < SP_MIN_N || rq->n > SP_MAX_N) return fail(e, SP_E_BAD_N, "n=%d outside [%d, %d]", rq->n, SP_MIN_N, SP_MAX_N);
+    if (rq->cmap_len < 2 || rq->cmap_len > SP_MAX_CMAP) return fail(e, SP_E_BAD_CMAP, "cmap_len=%d outside [2, %d]", rq->cmap_len, SP_MAX_CMAP);
+    if (rq->channel_mode && rq->n > 4096) return fail(e, SP_E_BAD_N, "channel_mode (split-real) is implemented for n <= 4096");
+    const uint64_t total_bytes = shard ? rq->total_byte_length : rq->byte_length;
+    const int64_t total_width = shard ? rq->total_width : rq->width;
+    if (total_bytes % (uint64_t)sp::element_size(rq->format))
+        return fail(e, SP_E_RAGGED, "byte length %llu is not a multiple of the %d-byte element size (typed array construction throws)",
+                    (unsigned long long)total_bytes, sp::element_size(rq->format));
+    if (total_width < 2) return fail(e, SP_E_BAD_WIDTH, "width=%lld: need at least 2 frames", (long long)total_width);
+    if (rq->width < 1) return fail(e, SP_E_BAD_WIDTH, "width=%lld", (long long)rq->width);
+    const double sc = (double)total_bytes / (double)sp::sample_width(rq->format);   // lib/samples.js:167
+    if (sc < (double)rq->n) return fail(e, SP_E_TOO_SHORT, "sampleCount %.1f < n %d", sc, rq->n);
+    if (!(rq->range != 0.0) || !std::isfinite(rq->range) || !std::isfinite(rq->gain) || !(rq->block_norm > 0.0))
+        return fail(e, SP_E_INVAL, "range must be finite and non-zero, gain finite, block_norm > 0");
+    *sample_count = sc;
+    *stride = (sc - (double)rq->n) / (double)(total_width - 1);                      // lib/worker.js:50
+    if (shard) {
+        if (rq->frame_first < 0 || rq->frame_first + rq->width > total_width)
+            return fail(e, SP_E_RANGE, "frame range [%lld, %lld) outside total width %lld", (long long)rq->frame_first,
+                        (long long)(rq->frame_first + rq->width), (long long)total_width);
+        // the shard buffer must cover every sample its frames read
+        const long long p_first = (long long)(0.5 + *stride * (double)rq->frame_first);
+        const long long p_last = (long long)(0.5 + *stride * (double)(rq->frame_first + rq->width - 1)) + rq->n;
+        const long long have_first = (long long)rq->buffer_first_sample;
+        const double have_last = (double)have_first + (double)rq->byte_length / sp::sample_width(rq->format);
+        if (p_first < have_first || ((double)p_last > have_last && (double)p_last <= sc))
+            return fail(e, SP_E_RANGE, "shard buffer [%lld, %.0f) does not cover samples [%lld, %lld) needed by its frames",
+                        have_first, have_last, p_first, p_last);
+    }
+    return SP_OK;
+}
+
+// Build the device-side job: upload constants, bind buffers.
+static int prepare(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, bool want_db, float *db_dev)
+{
+    const bool shard = rq->total_width != 0 || rq->total_byte_length != 0;
+    double sample_count = 0, stride = 0;
+    int rc = validate(e, rq, shard, &sample_count, &stride);
+    if (rc) return rc;
+    CU(cudaSetDevice(e->dev));
+    const int n = rq->n;
+    j.log2n = ilog2_exact(n);
+    j.plan = make_plan(j.log2n);
+    j.width = rq->width;
+    j.range = rq->range;
+    j.gain = rq->gain;
+    const bool in_dev = rq->flags & SP_F_BUFFER_ON_DEVICE, out_dev = rq->flags & SP_F_REPLY_ON_DEVICE;
+    Params &p = j.p;
+    memset(&p, 0, sizeof p);
+
+    // ---- input bytes
+    if (in_dev) {
+        if ((uintptr_t)rq->buffer & 15) return fail(e, SP_E_ALIGN, "device buffer must be 16-byte aligned");
+        p.buf = (const uint8_t *)rq->buffer;
+    } else {
+        if ((rc = ensure(e, e->in, rq->byte_length + 16))) return rc;
+        CU(cudaMemcpyAsync(e->in.p, rq->buffer, rq->byte_length, cudaMemcpyHostToDevice, e->stream));
+        p.buf = (const uint8_t *)e->in.p;
+    }
+    p.valid_bytes = rq->byte_length;
+    p.sample_base = shard ? (long long)rq->buffer_first_sample : 0;
+    p.format = rq->format;
+    p.n_full = n;
+    p.stride = stride;
+    p.frame_first = shard ? rq->frame_first : 0;
+    p.nframes = rq->width;
+    p.chunk_first = 0;
+    p.chunk_frames = rq->width;
+
+    // ---- window (fp32, rounded once), colour LUT, twiddles
+    {
+        std::vector<float> w((size_t)n);
+        for (int i = 0; i < n; i++) w[i] = (float)rq->windowc[i];
+        if ((rc = ensure(e, e->window, sizeof(float) * (size_t)n))) return rc;
+        CU(cudaMemcpyAsync(e->window.p, w.data(), sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+        std::vector<uint32_t> lut((size_t)rq->cmap_len);
+        for (int i = 0; i < rq->cmap_len; i++)          // R, G, B, A=255 in memory order (lib/worker.js:118-121)
+            lut[i] = (uint32_t)rq->cmap_rgb[3 * i] | ((uint32_t)rq->cmap_rgb[3 * i + 1] << 8) |
+                     ((uint32_t)rq->cmap_rgb[3 * i + 2] << 16) | 0xff000000u;
+        if ((rc = ensure(e, e->lut, sizeof(uint32_t) * (size_t)rq->cmap_len))) return rc;
+        CU(cudaMemcpyAsync(e->lut.p, lut.data(), sizeof(uint32_t) * (size_t)rq->cmap_len, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaStreamSynchronize(e->stream));          // the staging vectors die here
+    }
+    p.window = (const float *)e->window.p;
+    p.lut = (const uint32_t *)e->lut.p;
+    if ((rc = get_twiddles(e, 1 << j.plan.log2k, &p.tw))) return rc;
+
+    // ---- dB / colour constants (lib/worker.js:32,39,93,111)
+    const double block_norm_db = 10.0 * log10(rq->block_norm);
+    const double color_norm = (double)rq->cmap_len / -rq->range;
+    p.c0 = (float)block_norm_db;
+    p.c1 = (float)(5.0 * log10(2.0));
+    p.gn = (float)(-color_norm);                                    // grayU = cmax - (d0 + gain) * color_norm
+    p.gc = (float)((double)(rq->cmap_len - 1) - rq->gain * color_norm);
+    p.cmaxf = (float)(rq->cmap_len - 1);
+    p.cmap_len = rq->cmap_len;
+    p.waterfall = rq->waterfall ? 1 : 0;
+    p.channel_mode = rq->channel_mode ? 1 : 0;
+    p.sub_r = j.plan.sub_r;
+
+    // ---- outputs
+    const size_t W = (size_t)rq->width;
+    const bool want_image = rp->image && !(rq->flags & SP_F_NO_IMAGE) && !want_db;
+    if (want_image) {
+        if (out_dev) {
+            j.d_image = rp->image;
+        } else {
+            if ((rc = ensure(e, e->image, 4 * W * (size_t)n))) return rc;
+            j.d_image = (uint8_t *)e->image.p;
+        }
+    }
+    p.image = j.d_image;
+    if ((rc = ensure(e, e->fmin, 4 * W)) || (rc = ensure(e, e->fmax, 4 * W)) || (rc = ensure(e, e->fmid, 8 * W))) return rc;
+    p.fmin = (float *)e->fmin.p;
+    p.fmax = (float *)e->fmax.p;
+    p.fmid = (float2 *)e->fmid.p;
+    if ((rc = ensure(e, e->hist, 8 * (size_t)(SP_CB_HIST_SIZE + SP_MAX_CMAP)))) return rc;
+    if ((rc = ensure(e, e->stats, 16))) return rc;
+    if ((rc = ensure(e, e->gauges, 3 * W))) return rc;
+    if (out_dev) {
+        j.d_cb = rp->cB_hist ? (unsigned long long *)rp->cB_hist : (unsigned long long *)e->hist.p;
+        j.d_c = rp->c_hist ? (unsigned long long *)rp->c_hist : (unsigned long long *)e->hist.p + SP_CB_HIST_SIZE;
+        j.d_gmin = rp->gauge_mins; j.d_gmax = rp->gauge_maxs; j.d_gamp = rp->gauge_amps;
+    } else {
+        j.d_cb = (unsigned long long *)e->hist.p;
+        j.d_c = (unsigned long long *)e->hist.p + SP_CB_HIST_SIZE;
+        j.d_gmin = (uint8_t *)e->gauges.p; j.d_gmax = j.d_gmin + W; j.d_gamp = j.d_gmax + W;
+    }
+    p.cb_hist = j.d_cb;
+    p.c_hist = j.d_c;
+    j.d_stats = (double *)e->stats.p;
+    p.db_out = want_db ? db_dev : nullptr;
+    return SP_OK;
+}
+
+// Enqueue all kernels of a job on e->stream (bracketed by the timing events).
+static int enqueue(sp_engine *e, Job &j)
+{
+    Params &p = j.p;
+    const int fmt = p.format;
+    e->launches = 0;
+    CU(cudaEventRecord(e->ev0, e->stream));
+    CU(cudaMemsetAsync(j.d_cb, 0, 8 * SP_CB_HIST_SIZE, e->stream));
+    CU(cudaMemsetAsync(j.d_c, 0, 8 * (size_t)p.cmap_len, e->stream));
+    const size_t smem = sp::main_smem_bytes(j.plan.smem_x, p.cmap_len);
+    int occ = 0;
+    if (j.plan.sub_r == 1) {
+        render_fn fn = render_for(fmt);
+        if (!fn) return fail(e, SP_E_CUDA, "no render kernel linked for format %d", fmt);
+        CU(fn(j.plan.log2k, &p, 0, smem, e->stream, &occ));
+        if (occ < 1) return fail(e, SP_E_CUDA, "render kernel does not fit an SM (smem %zu)", smem);
+        p.ntiles = (p.chunk_frames + j.plan.tile - 1) / j.plan.tile;
+        const long long cap = (long long)e->sm_count * occ;
+        const int grid = (int)(p.ntiles < cap ? p.ntiles : cap);
+        CU(fn(j.plan.log2k, &p, grid, smem, e->stream, nullptr));
+        e->launches++;
+    } else {
+        // four-step path for n > 4096: radix-R pre-pass into an L2-sized scratch, then the
+        // 4096-point kernel in sub-frame mode, chunk by chunk
+        const int R = j.plan.sub_r;
+        const int n = p.n_full;
+        render_fn fn = sp_rl_cf32 ? sp_rl_cf32 : sp_rl_rt;   // sub-frame input is always complex fp32
+        prepass_fn pf = prepass_for(fmt);
+        if (!fn || !pf) return fail(e, SP_E_CUDA, "no kernels linked for the four-step path");
+        const float2 *tw_full = nullptr;
+        int rc = get_twiddles(e, n, &tw_full);
+        if (rc) return rc;
+        size_t scratch_mb = 96;
+        if (const char *s = getenv("SP_SCRATCH_MB")) scratch_mb = (size_t)atoi(s) > 0 ? (size_t)atoi(s) : scratch_mb;
+        long long ch = (long long)((scratch_mb << 20) / ((size_t)n * 8));
+        ch = ch / 8 * 8;
+        if (ch < 8) ch = 8;
+        if (ch > p.nframes) ch = (p.nframes + 7) / 8 * 8;
+        if ((rc = ensure(e, e->scratch, (size_t)ch * (size_t)n * 8))) return rc;
+        CU(fn(12, &p, 0, smem, e->stream, &occ));
+        if (occ < 1) return fail(e, SP_E_CUDA, "render kernel does not fit an SM (smem %zu)", smem);
+        const long long nf = p.nframes;
+        sp::init_minmax_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, e->stream>>>((unsigned *)p.fmin, (unsigned *)p.fmax, nf);
+        e->launches++;
+        for (long long c0 = 0; c0 < nf; c0 += ch) {
+            Params q = p;
+            q.chunk_first = c0;
+            q.chunk_frames = (nf - c0 < ch) ? nf - c0 : ch;
+            CU(pf(R, &q, (float2 *)e->scratch.p, tw_full, e->stream));
+            q.sub_in = (const float2 *)e->scratch.p;
+            q.ntiles = ((q.chunk_frames + 7) / 8) * R;
+            const long long cap = (long long)e->sm_count * occ;
+            const int grid = (int)(q.ntiles < cap ? q.ntiles : cap);
+            CU(fn(12, &q, grid, smem, e->stream, nullptr));
+            e->launches += 2;
+        }
+    }
+    sp::finalize_kernel<<<1, 1024, 0, e->stream>>>(p.fmin, p.fmax, p.fmid, p.nframes, j.range, j.gain, j.plan.sub_r > 1 ? 1 : 0,
+                                                   j.d_gmin, j.d_gmax, j.d_gamp, j.d_stats);
+    e->launches++;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(e->ev1, e->stream));
+    return SP_OK;
+}
+
+static int finish(sp_engine *e, sp_reply *rp)
+{
+    double st[2];
+    CU(cudaMemcpyAsync(st, e->stats.p, 16, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    rp->dBfs_min = st[0];
+    rp->dBfs_max = st[1];
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    rp->device_ms = ms;
+    rp->kernel_launches = e->launches;
+    return SP_OK;
+}
+
+extern "C" int sp_render_enqueue(sp_engine *e, const sp_request *rq, sp_reply *rp)
+{
+    if (!e || !rq || !rp) return fail(e, SP_E_INVAL, "null argument");
+    if (!(rq->flags & SP_F_BUFFER_ON_DEVICE) || !(rq->flags & SP_F_REPLY_ON_DEVICE))
+        return fail(e, SP_E_INVAL, "sp_render_enqueue needs SP_F_BUFFER_ON_DEVICE | SP_F_REPLY_ON_DEVICE");
+    Job j;
+    int rc = prepare(e, rq, rp, j, false, nullptr);
+    if (rc) return rc;
+    if ((rc = enqueue(e, j))) return rc;
+    e->pending = true;
+    return SP_OK;
+}
+
+extern "C" int sp_render_finish(sp_engine *e, sp_reply *rp)
+{
+    if (!e || !rp) return fail(e, SP_E_INVAL, "null argument");
+    if (!e->pending) return fail(e, SP_E_INVAL, "no render enqueued");
+    e->pending = false;
+    CU(cudaSetDevice(e->dev));
+    return finish(e, rp);
+}
+
+extern "C" int sp_render(sp_engine *e, const sp_request *rq, sp_reply *rp)
+{
+    if (!e || !rq || !rp) return fail(e, SP_E_INVAL, "null argument");
+    Job j;
+    int rc = prepare(e, rq, rp, j, false, nullptr);
+    if (rc) return rc;
+    if ((rc = enqueue(e, j))) return rc;
+    const size_t W = (size_t)rq->width;
+    if (!(rq->flags & SP_F_REPLY_ON_DEVICE)) {
+        if (j.d_image) CU(cudaMemcpyAsync(rp->image, j.d_image, 4 * W * (size_t)rq->n, cudaMemcpyDeviceToHost, e->stream));
+        if (rp->gauge_mins) CU(cudaMemcpyAsync(rp->gauge_mins, j.d_gmin, W, cudaMemcpyDeviceToHost, e->stream));
+        if (rp->gauge_maxs) CU(cudaMemcpyAsync(rp->gauge_maxs, j.d_gmax, W, cudaMemcpyDeviceToHost, e->stream));
+        if (rp->gauge_amps) CU(cudaMemcpyAsync(rp->gauge_amps, j.d_gamp, W, cudaMemcpyDeviceToHost, e->stream));
+        if (rp->cB_hist) CU(cudaMemcpyAsync(rp->cB_hist, j.d_cb, 8 * SP_CB_HIST_SIZE, cudaMemcpyDeviceToHost, e->stream));
+        if (rp->c_hist) CU(cudaMemcpyAsync(rp->c_hist, j.d_c, 8 * (size_t)rq->cmap_len, cudaMemcpyDeviceToHost, e->stream));
+    }
+    return finish(e, rp);
+}
+
+extern "C" int sp_render_db(sp_engine *e, const sp_request *rq, float *db)
+{
+    if (!e || !rq || !db) return fail(e, SP_E_INVAL, "null argument");
+    const size_t cnt = (size_t)rq->width * (size_t)rq->n;
+    int rc = ensure(e, e->db, cnt * 4);
+    if (rc) return rc;
+    sp_reply rp;
+    memset(&rp, 0, sizeof rp);
+    sp_request r2 = *rq;
+    r2.flags &= ~SP_F_REPLY_ON_DEVICE;
+    Job j;
+    if ((rc = prepare(e, &r2, &rp, j, true, (float *)e->db.p))) return rc;
+    if ((rc = enqueue(e, j))) return rc;
+    CU(cudaMemcpyAsync(db, e->db.p, cnt * 4, cudaMemcpyDeviceToHost, e->stream));
+    return finish(e, &rp);
+}
+
+extern "C" int sp_decode(sp_engine *e, int format, const void *bytes, uint64_t nbytes, uint64_t first, uint64_t count, float *iq)
+{
+    if (!e || !bytes || !iq) return fail(e, SP_E_INVAL, "null argument");
+    if (format < 0 || format >= SP_FORMAT_COUNT) return fail(e, SP_E_BAD_FORMAT, "format %d out of range", format);
+    if (count == 0) return SP_OK;
+    CU(cudaSetDevice(e->dev));
+    int rc;
+    if ((rc = ensure(e, e->in, nbytes + 16)) || (rc = ensure(e, e->db, count * 8))) return rc;
+    CU(cudaMemcpyAsync(e->in.p, bytes, nbytes, cudaMemcpyHostToDevice, e->stream));
+    sp::decode_kernel<<<(unsigned)((count + 255) / 256), 256, 0, e->stream>>>((const uint8_t *)e->in.p, nbytes, format,
+                                                                             (long long)first, (long long)count, (float2 *)e->db.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(iq, e->db.p, count * 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return SP_OK;
+}
+
+// ------------------------------------------------------------------ memory helpers
+extern "C" int sp_device_alloc(sp_engine *e, uint64_t nbytes, void **dptr)
+{
+    if (!e || !dptr) return SP_E_INVAL;
+    CU(cudaSetDevice(e->dev));
+    CU(cudaMalloc(dptr, (size_t)((nbytes + 255) & ~255ull) + 256));
+    return SP_OK;
+}
+extern "C" int sp_device_free(sp_engine *e, void *dptr)
+{
+    if (!e) return SP_E_INVAL;
+    CU(cudaSetDevice(e->dev));
+    CU(cudaFree(dptr));
+    return SP_OK;
+}
+extern "C" int sp_memcpy_h2d(sp_engine *e, void *dst, const void *src, uint64_t n)
+{
+    if (!e) return SP_E_INVAL;
+    CU(cudaSetDevice(e->dev));
+    CU(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return SP_OK;
+}
+extern "C" int sp_memcpy_d2h(sp_engine *e, void *dst, const void *src, uint64_t n)
+{
+    if (!e) return SP_E_INVAL;
+    CU(cudaSetDevice(e->dev));
+    CU(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return SP_OK;
+}
+extern "C" int sp_host_alloc_pinned(uint64_t n, void **hptr)
+{
+    if (!hptr) return SP_E_INVAL;
+    return cudaMallocHost(hptr, n) == cudaSuccess ? SP_OK : SP_E_CUDA;
+}
+extern "C" int sp_host_free_pinned(void *hptr) { return cudaFreeHost(hptr) == cudaSuccess ? SP_OK : SP_E_CUDA; }
+extern "C" int sp_device_sync(sp_engine *e)
+{
+    if (!e) return SP_E_INVAL;
+    CU(cudaSetDevice(e->dev));
+    CU(cudaStreamSynchronize(e->stream));
+    return SP_OK;
+}
+
+// ------------------------------------------------------------------ synthetic capture
+extern "C" void sp_synth_lut(int16_t *lut)
+{
+    for (int j = 0; j < 4096; j++) lut[j] = (int16_t)lround(32767.0 * sin(2.0 * M_PI * j / 4096.0));
+}
+
+extern "C" int sp_synth_fill(sp_engine *e, void *dst_dev, int format, uint64_t first, uint64_t count, uint64_t total_samples, uint64_t seed)
+{
+    if (!e || !dst_dev) return fail(e, SP_E_INVAL, "null argument");
+    if (format < 0 || format >= SP_FORMAT_COUNT) return fail(e, SP_E_BAD_FORMAT, "format %d out of range", format);
+    CU(cudaSetDevice(e->dev));
+    if (!e->synth_lut.p) {
+        int rc = ensure(e, e->synth_lut, 8192);
+        if (rc) return rc;
+        int16_t lut[4096];
+        sp_synth_lut(lut);
+        CU(cudaMemcpyAsync(e->synth_lut.p, lut, 8192, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    if (count == 0) return SP_OK;
+    unsigned long long blocks = (count + 255) / 256;
+    const unsigned long long cap = (unsigned long long)e->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    sp::synth_kernel<<<(unsigned)blocks, 256, 0, e->stream>>>((uint8_t *)dst_dev, format, first, count, total_samples, seed,
+                                                              (const short *)e->synth_lut.p);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(e->stream));
+    return SP_OK;
+}

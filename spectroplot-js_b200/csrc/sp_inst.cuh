@@ -1,0 +1,79 @@
+// sp_inst.cuh — per-format instantiation of the render / pre-pass kernels.
+// Each sp_inst_<fmt>.cu defines SP_INST_FMT and SP_INST_TAG and includes this file; the engine
+// binds the resulting entry points through weak symbols, so a build may carry any subset of
+// specialised formats next to the runtime-switch variant (tag "rt").
+#pragma once
+#include "sp_kernels.cuh"
+
+namespace sp {
+
+template <int LOG2N, int FMT>
+static cudaError_t launch_one(const Params &p, int grid, size_t smem, cudaStream_t st, int *occ_out)
+{
+    auto kfn = render_kernel<LOG2N, FMT>;
+    static bool attr_done = false;           // one engine call at a time (see header)
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    if (occ_out) {
+        int nb = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, 256, smem);
+        *occ_out = nb;
+        return e;
+    }
+    kfn<<<grid, 256, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int FMT>
+static cudaError_t launch_render(int log2n, const Params &p, int grid, size_t smem, cudaStream_t st, int *occ_out)
+{
+    switch (log2n) {
+    case 3: return launch_one<3, FMT>(p, grid, smem, st, occ_out);
+    case 4: return launch_one<4, FMT>(p, grid, smem, st, occ_out);
+    case 5: return launch_one<5, FMT>(p, grid, smem, st, occ_out);
+    case 6: return launch_one<6, FMT>(p, grid, smem, st, occ_out);
+    case 7: return launch_one<7, FMT>(p, grid, smem, st, occ_out);
+    case 8: return launch_one<8, FMT>(p, grid, smem, st, occ_out);
+    case 9: return launch_one<9, FMT>(p, grid, smem, st, occ_out);
+    case 10: return launch_one<10, FMT>(p, grid, smem, st, occ_out);
+    case 11: return launch_one<11, FMT>(p, grid, smem, st, occ_out);
+    case 12: return launch_one<12, FMT>(p, grid, smem, st, occ_out);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+template <int FMT>
+static cudaError_t launch_prepass(int r, const Params &p, float2 *out, const float2 *tw_full, cudaStream_t st)
+{
+    const long long threads = p.chunk_frames * 4096;
+    const int grid = (int)((threads + 255) / 256);
+    switch (r) {
+    case 2: prepass_kernel<2, FMT><<<grid, 256, 0, st>>>(p, out, tw_full); break;
+    case 4: prepass_kernel<4, FMT><<<grid, 256, 0, st>>>(p, out, tw_full); break;
+    case 8: prepass_kernel<8, FMT><<<grid, 256, 0, st>>>(p, out, tw_full); break;
+    case 16: prepass_kernel<16, FMT><<<grid, 256, 0, st>>>(p, out, tw_full); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+} // namespace sp
+
+#define SP_CAT2(a, b) a##b
+#define SP_CAT(a, b) SP_CAT2(a, b)
+
+#ifdef SP_INST_FMT
+extern "C" cudaError_t SP_CAT(sp_rl_, SP_INST_TAG)(int log2n, const sp::Params *p, int grid, size_t smem,
+                                                    cudaStream_t st, int *occ_out)
+{
+    return sp::launch_render<SP_INST_FMT>(log2n, *p, grid, smem, st, occ_out);
+}
+extern "C" cudaError_t SP_CAT(sp_pl_, SP_INST_TAG)(int r, const sp::Params *p, float2 *out, const float2 *tw_full,
+                                                    cudaStream_t st)
+{
+    return sp::launch_prepass<SP_INST_FMT>(r, *p, out, tw_full, st);
+}
+#endif

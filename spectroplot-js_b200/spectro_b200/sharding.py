@@ -1,0 +1,45 @@
+"""Frame-range sharding of one long message across GPUs.
+
+Unlike the reference's halo-free fan-out (lib/samples.js:253-258, lib/spectroplot.js:1206-1228),
+frames keep their GLOBAL positions p_x = ~~(0.5 + stride * x), so the union of the shards is the
+unsharded message bit for bit: images / gauges are disjoint column bands, histograms add, min/max
+fold.  A shard needs samples [p(x_first), p(x_last) + n): its own range plus a window-length halo.
+"""
+from __future__ import annotations
+
+
+def frame_pos(stride: float, x: int) -> int:
+    return int(0.5 + stride * x)             # lib/worker.js:72 (int64 instead of int32)
+
+
+def plan_shards(total_samples: int, n: int, total_width: int, world: int, align_samples: int = 16):
+    """-> list of dicts {frame_first, width, sample_first, sample_count} (contiguous frame ranges).
+    sample_first is rounded down to `align_samples` so any format's byte offset is 16-byte aligned."""
+    stride = (total_samples - n) / (total_width - 1)
+    out = []
+    for g in range(world):
+        x0 = g * total_width // world
+        x1 = (g + 1) * total_width // world
+        if x1 <= x0:
+            out.append(dict(frame_first=x0, width=0, sample_first=0, sample_count=0))
+            continue
+        s0 = frame_pos(stride, x0)
+        s1 = min(frame_pos(stride, x1 - 1) + n, total_samples)
+        s0 -= s0 % align_samples
+        out.append(dict(frame_first=x0, width=x1 - x0, sample_first=s0, sample_count=s1 - s0))
+    return out
+
+
+def shard_fields(shard: dict, total_samples: int, sample_width: int, total_width: int) -> dict:
+    """The sp_request shard_* fields for one planned shard."""
+    return dict(total_byte_length=total_samples * sample_width, total_width=total_width,
+                frame_first=shard["frame_first"], buffer_first_sample=shard["sample_first"])
+
+
+def merge_stats(parts):
+    """Fold per-shard replies like lib/spectroplot.js:1229-1238: histograms add, min/max fold."""
+    cB = sum(p["cB_hist"] for p in parts[1:]) + parts[0]["cB_hist"] if len(parts) > 1 else parts[0]["cB_hist"].copy()
+    c = sum(p["c_hist"] for p in parts[1:]) + parts[0]["c_hist"] if len(parts) > 1 else parts[0]["c_hist"].copy()
+    mn = min([0.0] + [p["dBfs_min"] for p in parts])
+    mx = max([-200.0] + [p["dBfs_max"] for p in parts])
+    return dict(cB_hist=cB, c_hist=c, dBfs_min=mn, dBfs_max=mx)

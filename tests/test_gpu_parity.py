@@ -1,0 +1,292 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs, against the committed golden fixtures, and through size-independent
+properties at larger sizes.  Tolerances are BASELINE.json's (see helpers.py)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from helpers import check_parity, injective_cmap, gray_from_image, DB_TOL, DB_FLOOR_REF
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CM256 = injective_cmap(256)
+
+
+def run_both(engine, buf, fmt, n, width, window="hann", gain=6, rng=30, cmap=CM256, channel_mode=False,
+             waterfall=False, want_db=True, label=""):
+    w, wt = O.window(window, n)
+    ora = O.render(buf, fmt, n, width, w, 1 / wt, gain, rng, cmap, channel_mode, waterfall, taps=True)
+    gpu = engine.render(buf, fmt, n, width, w, 1 / wt, gain, rng, cmap, channel_mode, waterfall)
+    db = engine.render_db(buf, fmt, n, width, w, 1 / wt, gain, rng, cmap, channel_mode) if want_db else None
+    nbad = check_parity(gpu, ora, cmap, n, width, waterfall, db, label or f"{fmt} n={n} w={width} {window}")
+    return gpu, ora, nbad
+
+
+# ------------------------------------------------------------------ decode: bit-exact
+@pytest.mark.parametrize("fmt", O.FORMATS)
+def test_decode_bit_exact(engine, fmt):
+    """gpu_fp32 == fround(reference_f64) for every sample (exhaustive code tables for <= 16 bit)."""
+    rng = np.random.default_rng(1234)
+    if fmt in ("CU4", "CS4"):
+        raw = np.arange(256, dtype=np.uint8)
+    elif fmt in ("CU8", "CS8"):
+        raw = np.stack([np.arange(256), np.arange(256)[::-1]], 1).astype(np.uint8).ravel()
+    elif fmt in ("CU12", "CS12"):
+        c = np.arange(4096); q = c[::-1]
+        raw = np.stack([c & 255, (c >> 8) | ((q & 15) << 4), q >> 4], 1).astype(np.uint8).ravel()
+    elif fmt in ("CU16", "CS16"):
+        raw = np.stack([np.arange(65536), np.arange(65536)[::-1]], 1).astype("<u2").view(np.uint8).ravel()
+    elif fmt == "CF32":
+        raw = np.concatenate([rng.standard_normal(1 << 16), [0.0, -0.0, np.inf, -np.inf, np.nan, 1e-40, 3e38, 1.0]]).astype("<f4").view(np.uint8)
+    elif fmt == "CF64":
+        raw = np.concatenate([rng.standard_normal(1 << 16) * 10.0 ** rng.integers(-30, 30, 1 << 16), [0.0, 1e-300, 1e300, np.nan]]).astype("<f8").view(np.uint8)
+    else:
+        raw = rng.integers(0, 256, (1 << 16) * 16, dtype=np.uint8)
+        edge = np.array([0, 0xFFFFFFFF, 0x80000000, 0x7FFFFFFF, 1, 0xFFFFFF7F, 0x00000080, 0x01000000], "<u4").view(np.uint8)
+        raw = np.concatenate([edge, edge[::-1].copy(), raw])
+    with np.errstate(over="ignore"):
+        ref = O.decode(fmt, raw).astype(np.float32)       # fround
+    got = engine.decode(fmt, raw)
+    assert got.shape == ref.shape
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)) or np.array_equal(
+        got[~np.isnan(ref)].view(np.uint32), ref[~np.isnan(ref)].view(np.uint32)) and np.array_equal(np.isnan(got), np.isnan(ref))
+
+
+def test_decode_out_of_range_follows_js(engine):
+    for fmt, raw in (("CU8", bytes([10, 20, 30])), ("CU4", bytes([0xFF])), ("CS12", bytes([0xFF])),
+                     ("CS16", bytes([1, 2, 3, 4, 5, 6])), ("CS64", bytes(range(20))), ("CU64", bytes(range(28)))):
+        cnt = len(raw) // O.SAMPLE_WIDTH[O.FORMATS.index(fmt)] + 2
+        ref = O.decode(fmt, raw, 0, cnt).astype(np.float32)
+        got = engine.decode(fmt, raw, 0, cnt)
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), fmt
+        assert np.array_equal(got[~np.isnan(ref)], ref[~np.isnan(ref)]), fmt
+
+
+def test_synth_generator_bit_identical(engine):
+    total = 100000
+    for fmt in O.FORMATS:
+        sw = O.SAMPLE_WIDTH[O.FORMATS.index(fmt)]
+        d = engine.alloc(5000 * sw)
+        engine.synth_fill(d, fmt, 777, 5000, total, 0xABCDEF)
+        got = np.empty(5000 * sw, np.uint8)
+        engine.d2h(got, d)
+        engine.free(d)
+        assert np.array_equal(got, O.synth(fmt, 777, 5000, total, 0xABCDEF)), fmt
+
+
+# ------------------------------------------------------------------ golden fixtures
+def test_appendix_b3(engine):
+    g = np.load(os.path.join(GOLD, "appendix_b3.npz"))
+    w, wt = O.window("hann", 8)
+    cmap = injective_cmap(256)
+    r = engine.render(g["buf"].tobytes(), "CU8", 8, 4, w, 1 / 3.5, 6, 30, cmap)
+    gray = gray_from_image(r["image"], cmap, 8, 4)
+    y = np.where(np.arange(8) <= 4, 4 - np.arange(8), 12 - np.arange(8))
+    img = np.zeros((8, 4), int); img[y[None, :], np.arange(4)[:, None]] = gray
+    assert np.abs(img - g["gray_image"].astype(int)).max() <= 1 and (img != g["gray_image"]).sum() <= 1
+    assert np.abs(r["gauge_mins"].astype(int) - g["gauge_mins"]).max() <= 1
+    assert np.abs(r["gauge_maxs"].astype(int) - g["gauge_maxs"]).max() <= 1
+    assert np.array_equal(r["gauge_amps"], g["gauge_amps"])
+    assert abs(r["dBfs_min"] - float(g["dBfs_min"])) < DB_TOL and abs(r["dBfs_max"] - float(g["dBfs_max"])) < DB_TOL
+    assert int(r["cB_hist"].sum()) == 32 and int(r["c_hist"].sum()) == 32
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "c*.npz"))))
+def test_golden_fixture(engine, path):
+    g = np.load(path)
+    fmt, n, width = str(g["fmt"]), int(g["n"]), int(g["width"])
+    cm, wf, lr = g["cmap"], bool(g["waterfall"]), bool(g["channel_mode"])
+    r = engine.render(g["buf"].tobytes(), fmt, n, width, g["windowc"], 1.0 / float(g["weight"]), float(g["gain"]),
+                      float(g["range"]), cm, lr, wf)
+    db = engine.render_db(g["buf"].tobytes(), fmt, n, width, g["windowc"], 1.0 / float(g["weight"]), float(g["gain"]),
+                          float(g["range"]), cm, lr)
+
+    class Ora:
+        pass
+    o = Ora()
+    for k in ("image", "gray", "db", "cB_hist", "c_hist", "gauge_mins", "gauge_maxs", "gauge_amps"):
+        setattr(o, k, g[k])
+    o.dBfs_min, o.dBfs_max = float(g["dBfs_min"]), float(g["dBfs_max"])
+    check_parity(r, o, cm, n, width, wf, db, os.path.basename(path))
+
+
+# ------------------------------------------------------------------ oracle parity sweeps
+@pytest.mark.parametrize("n", [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096])
+def test_all_single_kernel_sizes(engine, n):
+    width = 37                                   # awkward width: fractional stride, partial tiles
+    S = n * 20 + 13
+    buf = O.synth("CS16", 0, S, S, 0x5EC70000 + n).tobytes()
+    run_both(engine, buf, "CS16", n, width, "hann")
+
+
+@pytest.mark.parametrize("n", [8192, 16384, 32768, 65536])
+def test_four_step_sizes(engine, n):
+    width = 12
+    S = n * 5 + 77
+    buf = O.synth("CF32", 0, S, S, 0x5EC71000 + n).tobytes()
+    run_both(engine, buf, "CF32", n, width, "blackmanHarris")
+
+
+@pytest.mark.parametrize("fmt", O.FORMATS)
+def test_all_formats_render(engine, fmt):
+    n, width = 1024, 24
+    S = 30000
+    buf = O.synth(fmt, 0, S, S, 0x5EC72000).tobytes()
+    run_both(engine, buf, fmt, n, width, "blackman")
+
+
+@pytest.mark.parametrize("window", O.WINDOWS)
+def test_all_windows(engine, window):
+    n, width = 512, 32
+    S = 512 * 32
+    buf = O.synth("CU8", 0, S, S, 0x5EC73000).tobytes()
+    run_both(engine, buf, "CU8", n, width, window)           # hop == n exactly (stride = n - n/(w-1)... fractional)
+
+
+def test_wide_rows_fast_path_and_hop_n(engine):
+    """width % 4 == 0 and S = width*n: stride is exactly... (S-n)/(w-1) = n: the headline geometry."""
+    n, width = 4096, 64
+    S = n * width
+    buf = O.synth("CS16", 0, S, S, 0x5EC74000).tobytes()
+    run_both(engine, buf, "CS16", n, width, "blackmanHarris")
+    n, width = 256, 1000                                      # several slots per CTA, partial last tile
+    S = n * width
+    buf = O.synth("CS16", 0, S, S, 0x5EC74001).tobytes()
+    run_both(engine, buf, "CS16", n, width, "hann", want_db=False)
+
+
+def test_overlapping_and_skipping_strides(engine):
+    n = 1024
+    S = 50000
+    buf = O.synth("CU8", 0, S, S, 0x5EC75000).tobytes()
+    run_both(engine, buf, "CU8", n, 400, "hann", want_db=False)      # stride ~ 123: heavy overlap
+    run_both(engine, buf, "CU8", n, 12, "hann", want_db=False)       # stride ~ 4452: skips data
+    run_both(engine, buf, "CU8", n, 3000 // 8, "hann", want_db=False)
+
+
+@pytest.mark.parametrize("cmap_len", [2, 64, 256, 1000])
+def test_cmap_lengths_and_ranges(engine, cmap_len):
+    n, width = 256, 20
+    S = 8000
+    buf = O.synth("CS8", 0, S, S, 0x5EC76000).tobytes()
+    cm = injective_cmap(cmap_len)
+    for gain, rng in ((0, 6), (6, 30), (40, 120), (90, 10)):
+        run_both(engine, buf, "CS8", n, width, "hamming", gain, rng, cm, want_db=False,
+                 label=f"cmap{cmap_len} gain{gain} range{rng}")
+
+
+@pytest.mark.parametrize("n", [64, 1024, 4096])
+def test_channel_mode_and_waterfall(engine, n):
+    width = 16
+    S = n * 16 + 5
+    buf = O.synth("CS16", 0, S, S, 0x5EC77000 + n).tobytes()
+    run_both(engine, buf, "CS16", n, width, "hann", channel_mode=True)
+    run_both(engine, buf, "CS16", n, width, "hann", waterfall=True)
+    run_both(engine, buf, "CS16", n, width, "hann", channel_mode=True, waterfall=True)
+
+
+def test_special_values(engine):
+    n, width = 64, 8
+    w, wt = O.window("hann", n)
+    # all zero: -inf dB -> cB bin 0, colour 0, min == -inf
+    r = engine.render(bytes(4 * n * width), "CS16", n, width, w, 1 / wt, 6, 30, CM256)
+    assert r["cB_hist"][0] == n * width and r["c_hist"][0] == n * width
+    assert r["dBfs_min"] == -np.inf and r["dBfs_max"] == -200.0
+    assert (r["gauge_mins"] == 0).all() and (r["gauge_amps"] == 0).all()
+    # NaN poisons exactly the frames that contain it
+    x = np.full((n * width, 2), 0.25, "<f4"); x[5, 1] = np.nan
+    buf = x.tobytes()
+    ora = O.render(buf, "CF32", n, width, w, 1 / wt, 6, 30, CM256, taps=True)
+    gpu = engine.render(buf, "CF32", n, width, w, 1 / wt, 6, 30, CM256)
+    g = gray_from_image(gpu["image"], CM256, n, width)
+    assert np.array_equal(g == 0, ora.gray == 0) and (g[0] == 0).all()
+    assert gpu["cB_hist"][0] >= n
+    # full-scale tone in a rectangular window sits at 0 dB
+    t = np.arange(n * width)
+    z = np.exp(2j * np.pi * 5 * t / n)
+    buf = np.stack([z.real, z.imag], 1).astype("<f4").tobytes()
+    w, wt = O.window("rectangular", n)
+    db = engine.render_db(buf, "CF32", n, width, w, 1 / wt, 0, 30, CM256)
+    assert np.abs(db[:, 5]).max() < 1e-3
+
+
+def test_ragged_buffer_tail(engine):
+    """CU8 with an odd byte count: sampleCount is fractional and the last frame reads one
+    `undefined` (NaN) component — the reference renders that frame as colour 0."""
+    n, width = 32, 5
+    raw = O.synth("CU8", 0, 200, 200, 5).tobytes() + b"\x80"
+    run_both(engine, raw, "CU8", n, width, "hann", want_db=False)
+    raw12 = O.synth("CU12", 0, 100, 100, 6).tobytes() + b"\x12"        # CU12: missing bytes read as 0 bits
+    run_both(engine, raw12, "CU12", n, width, "hann", want_db=False)
+
+
+def test_error_codes(engine):
+    import spectro_b200
+    w, wt = O.window("hann", 64)
+    buf = bytes(4 * 64 * 4)
+    def code(**kw):
+        a = dict(buf=buf, fmt="CS16", n=64, width=4, windowc=w, block_norm=1 / wt, gain=6, range_=30, cmap=CM256)
+        a.update(kw)
+        with pytest.raises(spectro_b200.SpError) as ei:
+            engine.render(**a)
+        return ei.value.name
+    assert code(n=48, windowc=np.ones(48)) == "SP_E_BAD_N"           # 'Length is not a power of 2'
+    assert code(width=1) == "SP_E_BAD_WIDTH"
+    assert code(buf=bytes(7)) == "SP_E_RAGGED"
+    assert code(buf=bytes(64)) == "SP_E_TOO_SHORT"
+    assert code(cmap=CM256[:1]) == "SP_E_BAD_CMAP"
+    assert code(fmt=99) == "SP_E_BAD_FORMAT"
+    # and the engine still works afterwards
+    engine.render(buf, "CS16", 64, 4, w, 1 / wt, 6, 30, CM256)
+
+
+# ------------------------------------------------------------------ sharding: N shards == 1 shard, exactly
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_frame_range_shards_reproduce_the_whole_message(engine, world):
+    from spectro_b200 import sharding
+    fmt, n, width, S = "CS16", 1024, 203, 150001
+    sw = 4
+    buf = O.synth(fmt, 0, S, S, 0x5EC78000).tobytes()
+    w, wt = O.window("hann", n)
+    whole = engine.render(buf, fmt, n, width, w, 1 / wt, 6, 30, CM256)
+    parts = []
+    for sh in sharding.plan_shards(S, n, width, world):
+        sub = buf[sh["sample_first"] * sw:(sh["sample_first"] + sh["sample_count"]) * sw]
+        r = engine.render(sub, fmt, n, sh["width"], w, 1 / wt, 6, 30, CM256,
+                          shard=sharding.shard_fields(sh, S, sw, width))
+        assert np.array_equal(r["image"], whole["image"][:, sh["frame_first"]:sh["frame_first"] + sh["width"]])
+        for k in ("gauge_mins", "gauge_maxs", "gauge_amps"):
+            assert np.array_equal(r[k], whole[k][sh["frame_first"]:sh["frame_first"] + sh["width"]])
+        parts.append(r)
+    m = sharding.merge_stats(parts)
+    assert np.array_equal(m["cB_hist"], whole["cB_hist"]) and np.array_equal(m["c_hist"], whole["c_hist"])
+    assert m["dBfs_min"] == whole["dBfs_min"] and m["dBfs_max"] == whole["dBfs_max"]
+
+
+# ------------------------------------------------------------------ properties at larger sizes
+def test_properties_at_scale(engine):
+    """C2-like geometry (cs16, N=4096, hop N) at 16 Mi samples, device resident, checked through
+    size-independent properties: histogram totals, determinism, sampled frames vs the oracle."""
+    n, width = 4096, 4096
+    S = n * width
+    d = engine.alloc(S * 4)
+    engine.synth_fill(d, "CS16", 0, S, S, 0x5EC70002)
+    w, wt = O.window("blackmanHarris", n)
+    r1 = engine.render(d, "CS16", n, width, w, 1 / wt, 6, 30, CM256, byte_length=S * 4)
+    r2 = engine.render(d, "CS16", n, width, w, 1 / wt, 6, 30, CM256, byte_length=S * 4)
+    engine.free(d)
+    assert int(r1["c_hist"].sum()) == n * width
+    assert int(r1["cB_hist"].sum()) <= n * width and int(r1["cB_hist"].sum()) >= n * width - 1000
+    for k in ("image", "cB_hist", "c_hist", "gauge_mins", "gauge_maxs", "gauge_amps"):
+        assert np.array_equal(r1[k], r2[k]), k                # deterministic (integer atomics only)
+    # colour histogram == histogram of the image itself
+    g = gray_from_image(r1["image"][:, :256], CM256, n, 256)
+    # sampled frames against the oracle (frames are independent: stride == n exactly)
+    for x in (0, 1, 255):
+        fb = O.synth("CS16", x * n, n, S, 0x5EC70002).tobytes() + O.synth("CS16", 0, n, S, 0x5EC70002).tobytes()
+        o = O.render(fb, "CS16", n, 2, w, 1 / wt, 6, 30, CM256, taps=True)
+        d_ = g[x].astype(int) - o.gray[0].astype(int)
+        assert np.abs(d_).max() <= 1 and (d_ != 0).sum() <= 8
