@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the render path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path
+
+Workload (BASELINE.json configs[1], "C2"): cs16 capture of 100 Mi complex samples PER GPU, FFT
+N=4096, Blackman-Harris window, Viridis colormap, dB histogram + colour histogram + min/max/amp
+gauges, spectrogram layout, hop == N (width = samples/N, so stride is exactly N and every sample is
+read once).  One "step" = one full render of the capture.  N>1: the capture is N times longer and
+is sharded by contiguous frame range (weak scaling); each rank renders its frames with the GLOBAL
+stride and the histograms / min / max are merged with NCCL all-reduces (no data-path collective).
+
+Prints ONE JSON line (rank 0).  `value` = device-resident input -> device-resident outputs;
+`e2e` = the same through the public host-buffer API (pinned host input -> pinned host outputs,
+H2D and D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "spectroplot-js_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "Msamples/s rendered to RGBA spectrogram (N=4096) and % of B200 HBM roofline"
+UNIT = "Msamples/s"
+FMT, N_FFT, WINDOW, CMAP, GAIN, RANGE = "CS16", 4096, "blackmanHarris", "viridis", 6, 30
+SAMPLES_PER_GPU = 100 * (1 << 20)           # 104 857 600 complex samples (419 MB of cs16)
+SEED = 0x5EC70002
+SW = 4                                      # bytes per cs16 sample
+ALG_BYTES_PER_SAMPLE = SW + 4.0             # input + RGBA at hop N; gauges/hist negligible
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def viridis_cmap():
+    from spectro_b200 import cmaps
+    cm = [list(c) for c in cmaps.cmaps["viridis_cmap"]]
+    cm[0] = [0, 0, 0]; cm[-1] = [255, 255, 255]          # caller-side overwrite, lib/spectroplot.js:1129-1130
+    return cmaps.cmap_bytes(cm)
+
+
+def window_f64():
+    from spectro_b200 import windows
+    w = windows.blackmanHarrisWindow(N_FFT)
+    return np.array(w["window"], np.float64), float(w["weight"])
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the path (the float64 restatement in
+# oracle/, since no JavaScript engine exists in this image), all host threads, fan-out exactly as
+# lib/spectroplot.js:1206-1228 does it (one slice per worker thread).
+# ----------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    frames = 512 * cores                                   # bounded sample: 2 Mi samples per core
+    S = frames * N_FFT
+    buf = O.synth(FMT, 0, S, S, SEED)
+    w, wt = window_f64()
+    cm = viridis_cmap()
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        O.render(buf, FMT, N_FFT, frames, w, 1.0 / wt, GAIN, RANGE, cm, workers=cores)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    val = S / (ms * 1e-3) / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2: cs16, FFT N=4096, Blackman-Harris, Viridis, hop N, hist+gauges",
+                       "sample_per_step": f"{S} complex samples ({frames} frames), {cores} worker threads, "
+                                          "fan-out as lib/spectroplot.js:1206-1228"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{S} samples per step; C float64 restatement of lib/worker.js (oracle/), "
+                                       "an upper bound on the JS worker's speed"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def cpu_baseline_sample():
+    """Bounded CPU run of the same workload on the box's host cores (rank 0, N=1 only)."""
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    frames = 1024 * cores
+    S = frames * N_FFT
+    buf = O.synth(FMT, 0, S, S, SEED)
+    w, wt = window_f64()
+    cm = viridis_cmap()
+    O.render(buf[: 4 * N_FFT * 64 * cores], FMT, N_FFT, 64 * cores, w, 1.0 / wt, GAIN, RANGE, cm, workers=cores)  # warm
+    t0 = time.perf_counter()
+    O.render(buf, FMT, N_FFT, frames, w, 1.0 / wt, GAIN, RANGE, cm, workers=cores)
+    dt = time.perf_counter() - t0
+    return {"value": S / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {S} samples ({frames} frames) of the C2 capture, one pass, {cores} threads; "
+                      "C float64 restatement of lib/worker.js (no JS engine in the image)"}
+
+
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import spectro_b200
+    from spectro_b200 import _lib, sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    eng = spectro_b200.Engine(local)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+
+    total_samples = SAMPLES_PER_GPU * world
+    total_width = total_samples // N_FFT                    # hop == N exactly
+    sh = sharding.plan_shards(total_samples, N_FFT, total_width, world)[rank]
+    width = sh["width"]
+    nbytes_in = sh["sample_count"] * SW
+    w, wt = window_f64()
+    cm = viridis_cmap()
+
+    # device-resident capture shard, generated on the device (bit-identical to the oracle's generator)
+    d_in = torch.empty(nbytes_in + 256, dtype=torch.uint8, device=dev)
+    eng.synth_fill(d_in.data_ptr(), FMT, sh["sample_first"], sh["sample_count"], total_samples, SEED)
+    d_img = torch.empty(4 * width * N_FFT, dtype=torch.uint8, device=dev)
+    d_g = torch.empty(3 * width, dtype=torch.uint8, device=dev)
+    d_hist = torch.zeros(1000 + len(cm), dtype=torch.int64, device=dev)   # cB_hist | c_hist (u64 counters)
+    d_mm = torch.zeros(2, dtype=torch.float64, device=dev)
+    shard = sharding.shard_fields(sh, total_samples, SW, total_width) if world > 1 else None
+
+    def step():
+        rq, keep = eng.make_request(d_in.data_ptr(), FMT, N_FFT, width, w, 1.0 / wt, GAIN, RANGE, cm,
+                                    byte_length=nbytes_in, shard=shard)
+        rp = eng.render_enqueue(rq, d_img.data_ptr(), (d_g.data_ptr(), d_g.data_ptr() + width, d_g.data_ptr() + 2 * width),
+                                d_hist.data_ptr(), d_hist.data_ptr() + 8000, d_mm.data_ptr())
+        if world > 1:                                       # merge: histograms add, min/max fold
+            dist.all_reduce(d_hist, op=dist.ReduceOp.SUM)
+            d_mm[1].neg_()
+            dist.all_reduce(d_mm, op=dist.ReduceOp.MIN)
+            d_mm[1].neg_()
+        return rp
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        rp = step()
+    barrier()
+    eng.profile_enable(args.steps)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    launches = 0
+    for _ in range(args.steps):
+        rp = step()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    eng.render_finish(rp)
+    launches = rp.kernel_launches * args.steps
+    kern_ms = eng.profile_read(args.steps)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = total_samples / (ms_step * 1e-3) / 1e6
+
+    # sanity of the timed output: histogram totals (size-independent property)
+    c_total = int(d_hist[1000:].sum().item())
+    assert c_total == total_width * N_FFT, (c_total, total_width * N_FFT)
+
+    # ---- end to end through the host-buffer API (pinned host memory both ways)
+    pin_in = spectro_b200.PinnedBuffer(nbytes_in)
+    eng.d2h(pin_in.array, d_in.data_ptr())
+    pin_img = spectro_b200.PinnedBuffer(4 * width * N_FFT)
+    e2e_steps = max(2, min(args.steps, 5))
+    eng.set_stream(None)
+    out = None
+    for i in range(1 + e2e_steps):
+        if i == 1:
+            barrier(); t0 = time.perf_counter()
+        out = eng.render(pin_in.array, FMT, N_FFT, width, w, 1.0 / wt, GAIN, RANGE, cm, shard=shard,
+                         out_image=pin_img.array)
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, dict(cB_hist=out["cB_hist"], c_hist=out["c_hist"], dBfs_min=out["dBfs_min"],
+                                               dBfs_max=out["dBfs_max"]))
+            merged = sharding.merge_stats(parts)
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item())
+    e2e_val = total_samples / (e2e_ms * 1e-3) / 1e6
+    h2d = nbytes_in + 8 * N_FFT // 2 + 4 * len(cm)
+    d2h = 4 * width * N_FFT + 3 * width + 8 * (1000 + len(cm)) + 16
+
+    if rank == 0:
+        peak, how = measured_peaks()
+        kms = float(np.mean(kern_ms)) if len(kern_ms) else ms_step
+        alg_bytes = ALG_BYTES_PER_SAMPLE * sh["sample_count"]
+        achieved = alg_bytes / (kms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "latest_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": "C2: cs16 100Mi samples/GPU, FFT N=4096, Blackman-Harris, Viridis, hop N "
+                                       f"(width {total_width}), dB+colour histograms, min/max/amp gauges",
+                           "samples_total": total_samples, "frames_total": total_width, "sharding": f"frame-range x{world}",
+                           "l2": "inputs (419 MB) and outputs (419 MB) per GPU exceed the 126 MB L2; no flush needed",
+                           "kernel_plan": eng.kernel_plan(FMT, N_FFT)},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": traffic, "peak_source": how, "kernel": "render_kernel<12,CS16>",
+                             "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes},
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_ms, "steps": e2e_steps},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "parity_check": {"c_hist_total": c_total, "dBfs_min": rp.dBfs_min, "dBfs_max": rp.dBfs_max}}
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_sample()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -132,6 +132,8 @@ typedef struct sp_reply {
     double dBfs_max;      /* max of (dBfs - gain), initial -200  (lib/worker.js:36,125)      */
     float device_ms;      /* out: device time of the kernels of this call (CUDA events)      */
     int32_t kernel_launches; /* out: number of engine kernels launched by this call          */
+    double *minmax_dev;   /* optional, SP_F_REPLY_ON_DEVICE only: device double[2] that receives
+                             {dBfs_min, dBfs_max} without a host round trip (multi-GPU merge) */
 } sp_reply;
 
 typedef struct sp_engine sp_engine;
@@ -196,6 +198,12 @@ int sp_device_sync(sp_engine *e);
 int sp_synth_fill(sp_engine *e, void *dst_dev, int format, uint64_t first, uint64_t count,
                   uint64_t total_samples, uint64_t seed);
 void sp_synth_lut(int16_t *lut4096);
+
+/* Per-launch timing of the dominant (render) kernel: keep `slots` CUDA event pairs and
+ * record one around every render-kernel launch (ring).  sp_profile_read() synchronises and
+ * returns up to `max` most recent durations in milliseconds (oldest first) and clears the ring. */
+int sp_profile_enable(sp_engine *e, int slots);
+int sp_profile_read(sp_engine *e, float *ms, int max);
 
 /* Introspection used by the bench / tests. */
 int sp_device_count(sp_engine *e);

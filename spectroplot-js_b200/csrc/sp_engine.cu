@@ -84,6 +84,11 @@ struct sp_engine {
     std::map<int, float2 *> tw;              // twiddle tables by n
     DevBuf in, image, fmin, fmax, fmid, gauges, hist, stats, lut, window, scratch, db, synth_lut;
     // state of an enqueued (not yet finished) render
+    std::vector<cudaEvent_t> prof0, prof1;   // per-launch timing ring of the render kernel
+    long long prof_count = 0;
+    std::vector<float> h_window;             // last uploaded window / LUT (upload only on change)
+    std::vector<uint32_t> h_lut;
+    double *stats_src = nullptr;
     bool pending = false;
     long long pend_width = 0;
     int pend_cmap_len = 0;
@@ -163,6 +168,8 @@ extern "C" void sp_destroy(sp_engine *e)
     DevBuf *bufs[] = { &e->in, &e->image, &e->fmin, &e->fmax, &e->fmid, &e->gauges, &e->hist, &e->stats,
                        &e->lut, &e->window, &e->scratch, &e->db, &e->synth_lut };
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+    for (auto ev : e->prof0) cudaEventDestroy(ev);
+    for (auto ev : e->prof1) cudaEventDestroy(ev);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -256,6 +263,16 @@ struct Job {
     double *d_stats = nullptr;
 };
 
+// bracket a render-kernel launch with the next event pair of the profiling ring
+static void prof_begin(sp_engine *e)
+{
+    if (!e->prof0.empty()) cudaEventRecord(e->prof0[e->prof_count % (long long)e->prof0.size()], e->stream);
+}
+static void prof_end(sp_engine *e)
+{
+    if (!e->prof0.empty()) { cudaEventRecord(e->prof1[e->prof_count % (long long)e->prof1.size()], e->stream); e->prof_count++; }
+}
+
 static int validate(sp_engine *e, const sp_request *rq, bool shard, double *sample_count, double *stride)
 {
     if (!rq->buffer || !rq->windowc || !rq->cmap_rgb) return fail(e, SP_E_INVAL, "buffer, windowc and cmap_rgb are required");
@@ -331,19 +348,34 @@ static int prepare(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, boo
     p.chunk_first = 0;
     p.chunk_frames = rq->width;
 
-    // ---- window (fp32, rounded once), colour LUT, twiddles
+    // ---- window (fp32, rounded once), colour LUT, twiddles.  Uploaded only when they change, from
+    // engine-owned staging vectors, so a steady stream of messages never synchronises the host here.
     {
-        std::vector<float> w((size_t)n);
-        for (int i = 0; i < n; i++) w[i] = (float)rq->windowc[i];
-        if ((rc = ensure(e, e->window, sizeof(float) * (size_t)n))) return rc;
-        CU(cudaMemcpyAsync(e->window.p, w.data(), sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
-        std::vector<uint32_t> lut((size_t)rq->cmap_len);
-        for (int i = 0; i < rq->cmap_len; i++)          // R, G, B, A=255 in memory order (lib/worker.js:118-121)
-            lut[i] = (uint32_t)rq->cmap_rgb[3 * i] | ((uint32_t)rq->cmap_rgb[3 * i + 1] << 8) |
-                     ((uint32_t)rq->cmap_rgb[3 * i + 2] << 16) | 0xff000000u;
-        if ((rc = ensure(e, e->lut, sizeof(uint32_t) * (size_t)rq->cmap_len))) return rc;
-        CU(cudaMemcpyAsync(e->lut.p, lut.data(), sizeof(uint32_t) * (size_t)rq->cmap_len, cudaMemcpyHostToDevice, e->stream));
-        CU(cudaStreamSynchronize(e->stream));          // the staging vectors die here
+        bool same_w = e->h_window.size() == (size_t)n;
+        if (same_w)
+            for (int i = 0; i < n; i++) if (e->h_window[i] != (float)rq->windowc[i]) { same_w = false; break; }
+        bool same_l = e->h_lut.size() == (size_t)rq->cmap_len;
+        if (same_l)
+            for (int i = 0; i < rq->cmap_len; i++) {
+                const uint32_t v = (uint32_t)rq->cmap_rgb[3 * i] | ((uint32_t)rq->cmap_rgb[3 * i + 1] << 8) |
+                                   ((uint32_t)rq->cmap_rgb[3 * i + 2] << 16) | 0xff000000u;
+                if (e->h_lut[i] != v) { same_l = false; break; }
+            }
+        if (!same_w || !same_l) CU(cudaStreamSynchronize(e->stream));   // staging vectors may still be in flight
+        if (!same_w) {
+            e->h_window.resize((size_t)n);
+            for (int i = 0; i < n; i++) e->h_window[i] = (float)rq->windowc[i];
+            if ((rc = ensure(e, e->window, sizeof(float) * (size_t)n))) return rc;
+            CU(cudaMemcpyAsync(e->window.p, e->h_window.data(), sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+        }
+        if (!same_l) {
+            e->h_lut.resize((size_t)rq->cmap_len);
+            for (int i = 0; i < rq->cmap_len; i++)          // R, G, B, A=255 in memory order (lib/worker.js:118-121)
+                e->h_lut[i] = (uint32_t)rq->cmap_rgb[3 * i] | ((uint32_t)rq->cmap_rgb[3 * i + 1] << 8) |
+                              ((uint32_t)rq->cmap_rgb[3 * i + 2] << 16) | 0xff000000u;
+            if ((rc = ensure(e, e->lut, sizeof(uint32_t) * (size_t)rq->cmap_len))) return rc;
+            CU(cudaMemcpyAsync(e->lut.p, e->h_lut.data(), sizeof(uint32_t) * (size_t)rq->cmap_len, cudaMemcpyHostToDevice, e->stream));
+        }
     }
     p.window = (const float *)e->window.p;
     p.lut = (const uint32_t *)e->lut.p;
@@ -392,7 +424,8 @@ static int prepare(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, boo
     }
     p.cb_hist = j.d_cb;
     p.c_hist = j.d_c;
-    j.d_stats = (double *)e->stats.p;
+    j.d_stats = (out_dev && rp->minmax_dev) ? rp->minmax_dev : (double *)e->stats.p;
+    e->stats_src = j.d_stats;
     p.db_out = want_db ? db_dev : nullptr;
     return SP_OK;
 }
@@ -416,7 +449,9 @@ static int enqueue(sp_engine *e, Job &j)
         p.ntiles = (p.chunk_frames + j.plan.tile - 1) / j.plan.tile;
         const long long cap = (long long)e->sm_count * occ;
         const int grid = (int)(p.ntiles < cap ? p.ntiles : cap);
+        prof_begin(e);
         CU(fn(j.plan.log2k, &p, grid, smem, e->stream, nullptr));
+        prof_end(e);
         e->launches++;
     } else {
         // four-step path for n > 4096: radix-R pre-pass into an L2-sized scratch, then the
@@ -450,7 +485,9 @@ static int enqueue(sp_engine *e, Job &j)
             q.ntiles = ((q.chunk_frames + 7) / 8) * R;
             const long long cap = (long long)e->sm_count * occ;
             const int grid = (int)(q.ntiles < cap ? q.ntiles : cap);
+            prof_begin(e);
             CU(fn(12, &q, grid, smem, e->stream, nullptr));
+            prof_end(e);
             e->launches += 2;
         }
     }
@@ -465,7 +502,7 @@ static int enqueue(sp_engine *e, Job &j)
 static int finish(sp_engine *e, sp_reply *rp)
 {
     double st[2];
-    CU(cudaMemcpyAsync(st, e->stats.p, 16, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(st, e->stats_src ? (void *)e->stats_src : e->stats.p, 16, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     rp->dBfs_min = st[0];
     rp->dBfs_max = st[1];
@@ -549,6 +586,37 @@ extern "C" int sp_decode(sp_engine *e, int format, const void *bytes, uint64_t n
     CU(cudaMemcpyAsync(iq, e->db.p, count * 8, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return SP_OK;
+}
+
+// ------------------------------------------------------------------ per-launch profiling ring
+extern "C" int sp_profile_enable(sp_engine *e, int slots)
+{
+    if (!e) return SP_E_INVAL;
+    CU(cudaSetDevice(e->dev));
+    for (auto ev : e->prof0) cudaEventDestroy(ev);
+    for (auto ev : e->prof1) cudaEventDestroy(ev);
+    e->prof0.clear(); e->prof1.clear(); e->prof_count = 0;
+    for (int i = 0; i < slots; i++) {
+        cudaEvent_t a, b;
+        CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+        e->prof0.push_back(a); e->prof1.push_back(b);
+    }
+    return SP_OK;
+}
+extern "C" int sp_profile_read(sp_engine *e, float *ms, int max)
+{
+    if (!e || !ms) return SP_E_INVAL;
+    CU(cudaSetDevice(e->dev));
+    CU(cudaStreamSynchronize(e->stream));
+    const long long slots = (long long)e->prof0.size();
+    long long have = e->prof_count < slots ? e->prof_count : slots;
+    if (have > max) have = max;
+    for (long long i = 0; i < have; i++) {
+        const long long idx = (e->prof_count - have + i) % slots;
+        CU(cudaEventElapsedTime(&ms[i], e->prof0[idx], e->prof1[idx]));
+    }
+    e->prof_count = 0;
+    return (int)have;
 }
 
 // ------------------------------------------------------------------ memory helpers

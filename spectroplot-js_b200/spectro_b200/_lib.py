@@ -32,7 +32,7 @@ SYMBOLS = ["sp_abi_version", "sp_format_from_name", "sp_format_name", "sp_sample
            "sp_create", "sp_destroy", "sp_last_error", "sp_set_stream", "sp_render", "sp_render_enqueue",
            "sp_render_finish", "sp_decode", "sp_render_db", "sp_device_alloc", "sp_device_free", "sp_memcpy_h2d",
            "sp_memcpy_d2h", "sp_host_alloc_pinned", "sp_host_free_pinned", "sp_device_sync", "sp_synth_fill",
-           "sp_synth_lut", "sp_device_count", "sp_sm_count", "sp_kernel_plan"]
+           "sp_synth_lut", "sp_device_count", "sp_sm_count", "sp_kernel_plan", "sp_profile_enable", "sp_profile_read"]
 
 
 class SpError(RuntimeError):
@@ -55,7 +55,7 @@ class Reply(C.Structure):
     _fields_ = [("image", C.c_void_p), ("gauge_mins", C.c_void_p), ("gauge_maxs", C.c_void_p),
                 ("gauge_amps", C.c_void_p), ("cB_hist", C.c_void_p), ("c_hist", C.c_void_p),
                 ("dBfs_min", C.c_double), ("dBfs_max", C.c_double), ("device_ms", C.c_float),
-                ("kernel_launches", C.c_int32)]
+                ("kernel_launches", C.c_int32), ("minmax_dev", C.c_void_p)]
 
 
 _lib = None
@@ -96,6 +96,8 @@ def load():
     lib.sp_synth_lut.argtypes = [C.c_void_p]
     lib.sp_synth_lut.restype = None
     lib.sp_format_from_name.argtypes = [C.c_char_p]
+    lib.sp_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    lib.sp_profile_read.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.sp_device_count.argtypes = [C.c_void_p]
     lib.sp_sm_count.argtypes = [C.c_void_p]
     _lib = lib
@@ -198,6 +200,30 @@ class Engine:
     def synth_fill(self, dptr: int, fmt, first: int, count: int, total: int, seed: int):
         self._check(self.lib.sp_synth_fill(self.h, C.c_void_p(dptr), format_id(fmt), first, count, total, seed))
 
+    def profile_enable(self, slots: int):
+        self._check(self.lib.sp_profile_enable(self.h, int(slots)))
+
+    def profile_read(self, max_n: int = 4096) -> np.ndarray:
+        out = np.zeros(max_n, np.float32)
+        n = self.lib.sp_profile_read(self.h, _vp(out), max_n)
+        if n < 0:
+            self._check(n)
+        return out[:n]
+
+    # ---- device-resident path (bench / multi-GPU host layer)
+    def render_enqueue(self, rq: "Request", image_dev=0, gauges_dev=(0, 0, 0), cB_dev=0, c_dev=0, minmax_dev=0) -> "Reply":
+        """Enqueue one render whose request buffer and reply buffers all live in HBM; no host sync."""
+        rq.flags |= F_BUFFER_ON_DEVICE | F_REPLY_ON_DEVICE
+        p = lambda v: C.c_void_p(int(v)) if v else None
+        rp = Reply(p(image_dev), p(gauges_dev[0]), p(gauges_dev[1]), p(gauges_dev[2]), p(cB_dev), p(c_dev),
+                   0.0, 0.0, 0.0, 0, p(minmax_dev))
+        self._check(self.lib.sp_render_enqueue(self.h, C.byref(rq), C.byref(rp)))
+        return rp
+
+    def render_finish(self, rp: "Reply") -> "Reply":
+        self._check(self.lib.sp_render_finish(self.h, C.byref(rp)))
+        return rp
+
     # ---- taps
     def decode(self, fmt, buf, first: int = 0, count: int | None = None) -> np.ndarray:
         f = format_id(fmt)
@@ -247,7 +273,7 @@ class Engine:
             img = out_image if out_image is not None else np.empty(4 * width * n, np.uint8)
         gmin = np.empty(width, np.uint8); gmax = np.empty(width, np.uint8); gamp = np.empty(width, np.uint8)
         cb = np.zeros(CB_HIST_SIZE, np.uint64); ch = np.zeros(rq.cmap_len, np.uint64)
-        rp = Reply(_vp(img), _vp(gmin), _vp(gmax), _vp(gamp), _vp(cb), _vp(ch), 0.0, 0.0, 0.0, 0)
+        rp = Reply(_vp(img), _vp(gmin), _vp(gmax), _vp(gamp), _vp(cb), _vp(ch), 0.0, 0.0, 0.0, 0, None)
         self._check(self.lib.sp_render(self.h, C.byref(rq), C.byref(rp)))
         if img is not None:
             img = img[: 4 * width * n].reshape((width, n, 4) if waterfall else (n, width, 4))

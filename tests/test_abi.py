@@ -44,7 +44,7 @@ def test_struct_layout_matches_header():
     from spectro_b200 import _lib
     # sizes implied by the header on LP64: request 14 x 8 = 120 bytes (with the 4 packed int32 pairs), reply 72
     assert C.sizeof(_lib.Request) == 120
-    assert C.sizeof(_lib.Reply) == 72
+    assert C.sizeof(_lib.Reply) == 80
     assert _lib.Request.windowc.offset == 56 and _lib.Request.total_byte_length.offset == 88
     assert _lib.Reply.dBfs_min.offset == 48 and _lib.Reply.device_ms.offset == 64
 
