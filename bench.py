@@ -180,7 +180,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     eng = spectro_b200.Engine(local)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream shared by torch (events, NCCL) and the engine (kernels)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     eng.set_stream(stream.cuda_stream)
 
     total_samples = SAMPLES_PER_GPU * world
@@ -206,10 +209,7 @@ def run_ours(args):
         rp = eng.render_enqueue(rq, d_img.data_ptr(), (d_g.data_ptr(), d_g.data_ptr() + width, d_g.data_ptr() + 2 * width),
                                 d_hist.data_ptr(), d_hist.data_ptr() + 8000, d_mm.data_ptr())
         if world > 1:                                       # merge: histograms add, min/max fold
-            dist.all_reduce(d_hist, op=dist.ReduceOp.SUM)
-            d_mm[1].neg_()
-            dist.all_reduce(d_mm, op=dist.ReduceOp.MIN)
-            d_mm[1].neg_()
+            sharding.allreduce_stats(dist, d_hist, d_mm)
         return rp
 
     def barrier():

@@ -21,15 +21,25 @@ __device__ __forceinline__ unsigned char u8clamped(double v)
 }
 
 // gauges (lib/worker.js:128-136) and the message-wide min / max (lib/worker.js:124-125).
-// One CTA; `ordered` says fmin/fmax hold f2ord() encodings (sub-frame mode).
-__global__ void __launch_bounds__(1024) finalize_kernel(const float *fmin, const float *fmax, const float2 *fmid,
-                                                        long long nframes, double range, double gain, int ordered,
-                                                        unsigned char *gmin, unsigned char *gmax, unsigned char *gamp,
-                                                        double *stats /* [2] min, max */)
+// Many CTAs of 256 frames each; the last CTA to finish converts the folded min/max to doubles.
+// `ordered` says fmin/fmax hold f2ord() encodings (sub-frame mode).  mm = {ordered min, ordered max,
+// done counter}, initialised by finalize_init_kernel.
+__global__ void finalize_init_kernel(unsigned *mm)
 {
-    __shared__ float s_mn[32], s_mx[32];
-    float mn = 0.0f, mx = -200.0f;                              // lib/worker.js:35-36
-    for (long long x = threadIdx.x; x < nframes; x += blockDim.x) {
+    mm[0] = f2ord(0.0f);        // lib/worker.js:35
+    mm[1] = f2ord(-200.0f);     // lib/worker.js:36
+    mm[2] = 0;
+}
+
+__global__ void __launch_bounds__(256) finalize_kernel(const float *fmin, const float *fmax, const float2 *fmid,
+                                                       long long nframes, double range, double gain, int ordered,
+                                                       unsigned char *gmin, unsigned char *gmax, unsigned char *gamp,
+                                                       unsigned *mm, double *stats /* [2] min, max */)
+{
+    __shared__ float s_mn[8], s_mx[8];
+    float mn = 0.0f, mx = -200.0f;
+    const long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < nframes) {
         const float a = ordered ? ord2f(reinterpret_cast<const unsigned *>(fmin)[x]) : fmin[x];
         const float b = ordered ? ord2f(reinterpret_cast<const unsigned *>(fmax)[x]) : fmax[x];
         mn = fminf(mn, a); mx = fmaxf(mx, b);
@@ -50,7 +60,14 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const float *fmin, const
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < (int)(blockDim.x / 32); w++) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); }
-        stats[0] = (double)mn; stats[1] = (double)mx;
+        atomicMin(&mm[0], f2ord(mn));
+        atomicMax(&mm[1], f2ord(mx));
+        __threadfence();
+        if (atomicAdd(&mm[2], 1u) == gridDim.x - 1) {          // last CTA: publish
+            __threadfence();
+            stats[0] = (double)ord2f(atomicMin(&mm[0], 0xffffffffu));
+            stats[1] = (double)ord2f(atomicMax(&mm[1], 0u));
+        }
     }
 }
 

@@ -36,6 +36,18 @@ __device__ __forceinline__ int js_trunc(float v)
     return (fabsf(v) < 2147483648.0f) ? r : 0;
 }
 
+// log2 for the dB conversion: one MUFU.LG2 (flush-to-zero variant: a power below 1.2e-38, i.e.
+// more than 60 dB below the -120 dBFS floor of the parity contract, reads as 0 -> -inf like an
+// exact zero).  Relative error 2^-22: 4e-7 dB.
+__device__ __forceinline__ float fast_log2(float x)
+{
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
 // ------------------------------------------------------------------ conversions (raw code -> fp32)
 // Each matches fround() of the reference's double expression for EVERY code (SURVEY A.1;
 // the three non-power-of-two biases need a correctly rounded IEEE division).
@@ -128,6 +140,52 @@ __device__ __forceinline__ float2 decode_fast(const uint8_t *__restrict__ buf, l
     } else {
         double2 v = *reinterpret_cast<const double2 *>(buf + 16 * s);
         return make_float2(__double2float_rn(v.x), __double2float_rn(v.y));
+    }
+}
+
+// ------------------------------------------------------------------ decode with the scale left out
+// For the formats whose scale is a power of two the multiplication by the scale commutes exactly
+// with the window product (fl(w * (c * 2^-k)) == fl((w * 2^-k) * c)), so the fused kernels fold it
+// into the fp32 window table and decode_raw() returns the integer code as a float.  Bit-exactness
+// of the decode itself is what decode_fast() (the sp_decode tap) states and tests.
+template <int FMT> __host__ __device__ constexpr float raw_scale()
+{
+    return FMT == CS4 ? 0.125f : FMT == CS8 ? 0.0078125f : FMT == CS12 ? 0.00048828125f
+         : FMT == CS16 ? 3.0517578125e-05f : FMT == CU16 ? 1.52587890625e-05f
+         : FMT == CS32 ? 4.656612873077393e-10f : 1.0f;
+}
+__host__ inline float raw_scale_rt(int fmt)
+{
+    switch (fmt) {
+    case CS4: return raw_scale<CS4>();   case CS8: return raw_scale<CS8>();   case CS12: return raw_scale<CS12>();
+    case CS16: return raw_scale<CS16>(); case CU16: return raw_scale<CU16>(); case CS32: return raw_scale<CS32>();
+    default: return 1.0f;
+    }
+}
+template <int FMT>
+__device__ __forceinline__ float2 decode_raw(const uint8_t *__restrict__ buf, long long s, int rt_fmt)
+{
+    if constexpr (FMT == CS4) {
+        int b = buf[s];
+        return make_float2((float)sext(b >> 4, 4), (float)sext(b & 15, 4));
+    } else if constexpr (FMT == CS8) {
+        unsigned v = *reinterpret_cast<const unsigned short *>(buf + 2 * s);
+        return make_float2((float)(int)(signed char)(v & 255), (float)(int)(signed char)(v >> 8));
+    } else if constexpr (FMT == CS12) {
+        const uint8_t *p = buf + 3 * s;
+        int b0 = p[0], b1 = p[1], b2 = p[2];
+        return make_float2((float)sext(((b1 & 15) << 8) | b0, 12), (float)sext((b2 << 4) | (b1 >> 4), 12));
+    } else if constexpr (FMT == CS16) {
+        unsigned v = *reinterpret_cast<const unsigned *>(buf + 4 * s);
+        return make_float2((float)(int)(short)(v & 0xffff), (float)((int)v >> 16));
+    } else if constexpr (FMT == CU16) {
+        unsigned v = *reinterpret_cast<const unsigned *>(buf + 4 * s);
+        return make_float2((float)(2 * (int)(v & 0xffff) - 65535), (float)(2 * (int)(v >> 16) - 65535));
+    } else if constexpr (FMT == CS32) {
+        uint2 v = *reinterpret_cast<const uint2 *>(buf + 8 * s);
+        return make_float2(__int2float_rn((int)v.x), __int2float_rn((int)v.y));
+    } else {
+        return decode_fast<FMT>(buf, s, rt_fmt);          // scale 1: the full decode
     }
 }
 

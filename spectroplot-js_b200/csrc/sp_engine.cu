@@ -5,6 +5,7 @@
 // No CPU fallback exists: without an sm_100 device sp_create fails with SP_E_NO_DEVICE.
 #include "../../include/spectro_b200.h"
 #include "sp_aux_kernels.cuh"
+#include "sp_kernel_big.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -21,12 +22,14 @@ using sp::Params;
 // ---- per-format kernel entry points (weak: a build may carry any subset, "rt" is mandatory) ----
 #define SP_DECL(tag)                                                                                             \
     extern "C" cudaError_t sp_rl_##tag(int, const Params *, int, size_t, cudaStream_t, int *) __attribute__((weak)); \
-    extern "C" cudaError_t sp_pl_##tag(int, const Params *, float2 *, const float2 *, cudaStream_t) __attribute__((weak));
+    extern "C" cudaError_t sp_pl_##tag(int, const Params *, float2 *, const float2 *, cudaStream_t) __attribute__((weak)); \
+    extern "C" cudaError_t sp_bl_##tag(int, const Params *, int, size_t, cudaStream_t, unsigned *, int *, int *) __attribute__((weak));
 SP_DECL(rt) SP_DECL(cu4) SP_DECL(cs4) SP_DECL(cu8) SP_DECL(cs8) SP_DECL(cu12) SP_DECL(cs12) SP_DECL(cu16)
 SP_DECL(cs16) SP_DECL(cu32) SP_DECL(cs32) SP_DECL(cu64) SP_DECL(cs64) SP_DECL(cf32) SP_DECL(cf64)
 
 typedef cudaError_t (*render_fn)(int, const Params *, int, size_t, cudaStream_t, int *);
 typedef cudaError_t (*prepass_fn)(int, const Params *, float2 *, const float2 *, cudaStream_t);
+typedef cudaError_t (*big_fn)(int, const Params *, int, size_t, cudaStream_t, unsigned *, int *, int *);
 
 static render_fn render_for(int fmt)
 {
@@ -39,6 +42,12 @@ static prepass_fn prepass_for(int fmt)
     static const prepass_fn tab[SP_FORMAT_COUNT] = { sp_pl_cu4, sp_pl_cs4, sp_pl_cu8, sp_pl_cs8, sp_pl_cu12, sp_pl_cs12,
         sp_pl_cu16, sp_pl_cs16, sp_pl_cu32, sp_pl_cs32, sp_pl_cu64, sp_pl_cs64, sp_pl_cf32, sp_pl_cf64 };
     return tab[fmt] ? tab[fmt] : sp_pl_rt;
+}
+static big_fn big_for(int fmt)
+{
+    static const big_fn tab[SP_FORMAT_COUNT] = { sp_bl_cu4, sp_bl_cs4, sp_bl_cu8, sp_bl_cs8, sp_bl_cu12, sp_bl_cs12,
+        sp_bl_cu16, sp_bl_cs16, sp_bl_cu32, sp_bl_cs32, sp_bl_cu64, sp_bl_cs64, sp_bl_cf32, sp_bl_cf64 };
+    return tab[fmt] ? tab[fmt] : sp_bl_rt;
 }
 static bool specialised(int fmt)
 {
@@ -81,8 +90,11 @@ struct sp_engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     std::string plan;
-    std::map<int, float2 *> tw;              // twiddle tables by n
-    DevBuf in, image, fmin, fmax, fmid, gauges, hist, stats, lut, window, scratch, db, synth_lut;
+    std::map<int, float2 *> tw, twA, twB;    // twiddle tables by n (full / pass A / pass B)
+    DevBuf tilectr, pin[2], pimg[2];         // pipeline: double-buffered input bytes / image tiles
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_comp[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr }, ev_setup = nullptr;
+    DevBuf in, image, fmin, fmax, fmid, gauges, hist, stats, mm, lut, window, scratch, db, synth_lut;
     // state of an enqueued (not yet finished) render
     std::vector<cudaEvent_t> prof0, prof1;   // per-launch timing ring of the render kernel
     long long prof_count = 0;
@@ -165,13 +177,24 @@ extern "C" void sp_destroy(sp_engine *e)
     cudaSetDevice(e->dev);
     cudaDeviceSynchronize();
     for (auto &kv : e->tw) cudaFree(kv.second);
-    DevBuf *bufs[] = { &e->in, &e->image, &e->fmin, &e->fmax, &e->fmid, &e->gauges, &e->hist, &e->stats,
-                       &e->lut, &e->window, &e->scratch, &e->db, &e->synth_lut };
+    for (auto &kv : e->twA) cudaFree(kv.second);
+    for (auto &kv : e->twB) cudaFree(kv.second);
+    DevBuf *bufs[] = { &e->in, &e->image, &e->fmin, &e->fmax, &e->fmid, &e->gauges, &e->hist, &e->stats, &e->mm,
+                       &e->lut, &e->window, &e->scratch, &e->db, &e->synth_lut, &e->tilectr, &e->pin[0], &e->pin[1],
+                       &e->pimg[0], &e->pimg[1] };
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (auto ev : e->prof0) cudaEventDestroy(ev);
     for (auto ev : e->prof1) cudaEventDestroy(ev);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    for (int i = 0; i < 2; i++) {
+        if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
+        if (e->ev_comp[i]) cudaEventDestroy(e->ev_comp[i]);
+        if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
+    }
+    if (e->ev_setup) cudaEventDestroy(e->ev_setup);
+    if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
+    if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -192,21 +215,55 @@ static int ilog2_exact(int n)
     return -1;
 }
 
+static int upload_table(sp_engine *e, std::map<int, float2 *> &cache, int key, const std::vector<float2> &h, const float2 **out)
+{
+    float2 *d = nullptr;
+    CU(cudaMalloc(&d, sizeof(float2) * h.size()));
+    CU(cudaMemcpyAsync(d, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    cache[key] = d;
+    *out = d;
+    return SP_OK;
+}
+static inline float2 twid(long long num, long long den)   // exp(-2 pi j num / den), double -> fp32 once
+{
+    const double a = 2.0 * M_PI * (double)(num % den) / (double)den;
+    return make_float2((float)cos(a), (float)-sin(a));
+}
+// full table W_n^i (pre-pass of the four-step sizes)
 static int get_twiddles(sp_engine *e, int n, const float2 **out)
 {
     auto it = e->tw.find(n);
     if (it != e->tw.end()) { *out = it->second; return SP_OK; }
     std::vector<float2> h((size_t)n);
-    for (int i = 0; i < n; i++) {                      // computed in double, rounded once
-        const double a = 2.0 * M_PI * (double)i / (double)n;
-        h[i] = make_float2((float)cos(a), (float)-sin(a));
+    for (int i = 0; i < n; i++) h[i] = twid(i, n);
+    return upload_table(e, e->tw, n, h, out);
+}
+// pass-A table [15][T]: W_N^{t*k}; pass-B table [15][RL]: W_{N/16}^{b*k}  (k = 1..15)
+static int get_pass_tables(sp_engine *e, int log2k, const float2 **twA, const float2 **twB)
+{
+    const int N = 1 << log2k;
+    *twA = *twB = nullptr;
+    if (log2k <= 4) return SP_OK;                        // single-pass sizes need no twiddles
+    const int T = N / 16;
+    auto it = e->twA.find(N);
+    if (it != e->twA.end()) *twA = it->second;
+    else {
+        std::vector<float2> h((size_t)15 * T);
+        for (int k = 1; k < 16; k++) for (int t = 0; t < T; t++) h[(size_t)(k - 1) * T + t] = twid((long long)t * k, N);
+        int rc = upload_table(e, e->twA, N, h, twA);
+        if (rc) return rc;
     }
-    float2 *d = nullptr;
-    CU(cudaMalloc(&d, sizeof(float2) * (size_t)n));
-    CU(cudaMemcpyAsync(d, h.data(), sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
-    e->tw[n] = d;
-    *out = d;
+    if (log2k <= 8) return SP_OK;
+    const int RL = N / 256, N1 = N / 16;
+    auto ib = e->twB.find(N);
+    if (ib != e->twB.end()) *twB = ib->second;
+    else {
+        std::vector<float2> h((size_t)15 * RL);
+        for (int k = 1; k < 16; k++) for (int b = 0; b < RL; b++) h[(size_t)(k - 1) * RL + b] = twid((long long)b * k, N1);
+        int rc = upload_table(e, e->twB, N, h, twB);
+        if (rc) return rc;
+    }
     return SP_OK;
 }
 
@@ -261,6 +318,7 @@ struct Job {
     uint8_t *d_gmin = nullptr, *d_gmax = nullptr, *d_gamp = nullptr;
     unsigned long long *d_cb = nullptr, *d_c = nullptr;
     double *d_stats = nullptr;
+    bool pipelined = false;    // host buffers streamed chunk by chunk: no whole-message device copies
 };
 
 // bracket a render-kernel launch with the next event pair of the profiling ring
@@ -293,6 +351,8 @@ static int validate(sp_engine *e, const sp_request *rq, bool shard, double *samp
     if (sc < (double)rq->n) return fail(e, SP_E_TOO_SHORT, "sampleCount %.1f < n %d", sc, rq->n);
     if (!(rq->range != 0.0) || !std::isfinite(rq->range) || !std::isfinite(rq->gain) || !(rq->block_norm > 0.0))
         return fail(e, SP_E_INVAL, "range must be finite and non-zero, gain finite, block_norm > 0");
+    if (10.0 * log10(rq->block_norm) < -75.0)
+        return fail(e, SP_E_INVAL, "block_norm %.3g is below -75 dB (1/weight of any window up to n = 65536 is above -49 dB)", rq->block_norm);
     *sample_count = sc;
     *stride = (sc - (double)rq->n) / (double)(total_width - 1);                      // lib/worker.js:50
     if (shard) {
@@ -333,6 +393,8 @@ static int prepare(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, boo
     if (in_dev) {
         if ((uintptr_t)rq->buffer & 15) return fail(e, SP_E_ALIGN, "device buffer must be 16-byte aligned");
         p.buf = (const uint8_t *)rq->buffer;
+    } else if (j.pipelined) {
+        p.buf = nullptr;                                   // set per chunk by render_pipelined
     } else {
         if ((rc = ensure(e, e->in, rq->byte_length + 16))) return rc;
         CU(cudaMemcpyAsync(e->in.p, rq->buffer, rq->byte_length, cudaMemcpyHostToDevice, e->stream));
@@ -351,9 +413,11 @@ static int prepare(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, boo
     // ---- window (fp32, rounded once), colour LUT, twiddles.  Uploaded only when they change, from
     // engine-owned staging vectors, so a steady stream of messages never synchronises the host here.
     {
+        // power-of-two sample scales are folded into the fp32 window (exact), see decode_raw()
+        const float wscale = specialised(rq->format) ? sp::raw_scale_rt(rq->format) : 1.0f;
         bool same_w = e->h_window.size() == (size_t)n;
         if (same_w)
-            for (int i = 0; i < n; i++) if (e->h_window[i] != (float)rq->windowc[i]) { same_w = false; break; }
+            for (int i = 0; i < n; i++) if (e->h_window[i] != (float)rq->windowc[i] * wscale) { same_w = false; break; }
         bool same_l = e->h_lut.size() == (size_t)rq->cmap_len;
         if (same_l)
             for (int i = 0; i < rq->cmap_len; i++) {
@@ -364,7 +428,7 @@ static int prepare(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, boo
         if (!same_w || !same_l) CU(cudaStreamSynchronize(e->stream));   // staging vectors may still be in flight
         if (!same_w) {
             e->h_window.resize((size_t)n);
-            for (int i = 0; i < n; i++) e->h_window[i] = (float)rq->windowc[i];
+            for (int i = 0; i < n; i++) e->h_window[i] = (float)rq->windowc[i] * wscale;
             if ((rc = ensure(e, e->window, sizeof(float) * (size_t)n))) return rc;
             CU(cudaMemcpyAsync(e->window.p, e->h_window.data(), sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
         }
@@ -379,7 +443,7 @@ static int prepare(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, boo
     }
     p.window = (const float *)e->window.p;
     p.lut = (const uint32_t *)e->lut.p;
-    if ((rc = get_twiddles(e, 1 << j.plan.log2k, &p.tw))) return rc;
+    if ((rc = get_pass_tables(e, j.plan.log2k, &p.twA, &p.twB))) return rc;
 
     // ---- dB / colour constants (lib/worker.js:32,39,93,111)
     const double block_norm_db = 10.0 * log10(rq->block_norm);
@@ -400,6 +464,8 @@ static int prepare(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, boo
     if (want_image) {
         if (out_dev) {
             j.d_image = rp->image;
+        } else if (j.pipelined) {
+            j.d_image = (uint8_t *)(uintptr_t)16;              // placeholder: per-chunk tiles (render_pipelined)
         } else {
             if ((rc = ensure(e, e->image, 4 * W * (size_t)n))) return rc;
             j.d_image = (uint8_t *)e->image.p;
@@ -411,7 +477,7 @@ static int prepare(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, boo
     p.fmax = (float *)e->fmax.p;
     p.fmid = (float2 *)e->fmid.p;
     if ((rc = ensure(e, e->hist, 8 * (size_t)(SP_CB_HIST_SIZE + SP_MAX_CMAP)))) return rc;
-    if ((rc = ensure(e, e->stats, 16))) return rc;
+    if ((rc = ensure(e, e->stats, 16)) || (rc = ensure(e, e->mm, 16))) return rc;
     if ((rc = ensure(e, e->gauges, 3 * W))) return rc;
     if (out_dev) {
         j.d_cb = rp->cB_hist ? (unsigned long long *)rp->cB_hist : (unsigned long long *)e->hist.p;
@@ -430,18 +496,60 @@ static int prepare(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, boo
     return SP_OK;
 }
 
-// Enqueue all kernels of a job on e->stream (bracketed by the timing events).
-static int enqueue(sp_engine *e, Job &j)
+// N = 4096 fast path (render_big_kernel): spectrogram layout, cmap_len <= 256, width % 4 == 0, image wanted.
+static bool big_eligible(const Params &p)
 {
-    Params &p = j.p;
-    const int fmt = p.format;
+    static const bool off = getenv("SP_NO_BIG") != nullptr;
+    return !off && p.image && !p.waterfall && !p.channel_mode && !p.db_out && p.cmap_len <= 256 && (p.nframes % 4 == 0) &&
+           (((uintptr_t)p.image) & 15) == 0;
+}
+static int big_variant()
+{
+    static const int v = getenv("SP_BIG_VARIANT") ? atoi(getenv("SP_BIG_VARIANT")) : 0;
+    return v;
+}
+static int launch_big_kernel(sp_engine *e, big_fn fn, Params &q)
+{
+    const int variant = big_variant();
+    const int slots = (variant == 1 || variant == 2) ? 3 : 2, f = (variant == 1 || variant == 3) ? 4 : 8;
+    int raw_bytes = 0, occ = 0;
+    CU(fn(variant, &q, 0, 0, e->stream, nullptr, nullptr, &raw_bytes));      // query RAW_BYTES
+    const size_t smem = sp::big_smem_bytes(raw_bytes, q.cmap_len, slots, f);
+    CU(fn(variant, &q, 0, smem, e->stream, nullptr, &occ, nullptr));
+    if (occ < 1) return fail(e, SP_E_CUDA, "render_big_kernel does not fit an SM (smem %zu)", smem);
+    int rc = ensure(e, e->tilectr, 256);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(e->tilectr.p, 0, 4, e->stream));
+    q.ntiles = ((q.chunk_frames + f - 1) / f) * (q.sub_r > 1 ? q.sub_r : 1);
+    const long long want = (q.ntiles + slots - 1) / slots;
+    const int grid = (int)(want < e->sm_count ? want : e->sm_count);
+    prof_begin(e);
+    CU(fn(variant, &q, grid, smem, e->stream, (unsigned *)e->tilectr.p, nullptr, nullptr));
+    prof_end(e);
+    return SP_OK;
+}
+
+// Enqueue all kernels of a job on e->stream (bracketed by the timing events).
+static int enqueue_begin(sp_engine *e, Job &j)
+{
     e->launches = 0;
     CU(cudaEventRecord(e->ev0, e->stream));
     CU(cudaMemsetAsync(j.d_cb, 0, 8 * SP_CB_HIST_SIZE, e->stream));
-    CU(cudaMemsetAsync(j.d_c, 0, 8 * (size_t)p.cmap_len, e->stream));
-    const size_t smem = sp::main_smem_bytes(j.plan.smem_x, p.cmap_len);
+    CU(cudaMemsetAsync(j.d_c, 0, 8 * (size_t)j.p.cmap_len, e->stream));
+    return SP_OK;
+}
+
+// the render kernels for the frames described by p (a whole message, a shard, or one pipeline chunk)
+static int enqueue_frames(sp_engine *e, Job &j, Params &p)
+{
+    const int fmt = p.format;
+    const size_t smem = sp::main_smem_bytes(j.plan.smem_x, p.cmap_len, j.plan.log2k > 8 ? 15 * ((1 << j.plan.log2k) / 256) : 0);
     int occ = 0;
-    if (j.plan.sub_r == 1) {
+    if (j.plan.sub_r == 1 && j.plan.log2k == 12 && big_eligible(p) && big_for(fmt)) {
+        int rc = launch_big_kernel(e, big_for(fmt), p);
+        if (rc) return rc;
+        e->launches++;
+    } else if (j.plan.sub_r == 1) {
         render_fn fn = render_for(fmt);
         if (!fn) return fail(e, SP_E_CUDA, "no render kernel linked for format %d", fmt);
         CU(fn(j.plan.log2k, &p, 0, smem, e->stream, &occ));
@@ -482,21 +590,146 @@ static int enqueue(sp_engine *e, Job &j)
             q.chunk_frames = (nf - c0 < ch) ? nf - c0 : ch;
             CU(pf(R, &q, (float2 *)e->scratch.p, tw_full, e->stream));
             q.sub_in = (const float2 *)e->scratch.p;
-            q.ntiles = ((q.chunk_frames + 7) / 8) * R;
-            const long long cap = (long long)e->sm_count * occ;
-            const int grid = (int)(q.ntiles < cap ? q.ntiles : cap);
-            prof_begin(e);
-            CU(fn(12, &q, grid, smem, e->stream, nullptr));
-            prof_end(e);
+            big_fn bf = sp_bl_cf32 ? sp_bl_cf32 : sp_bl_rt;
+            if (big_eligible(q) && bf) {
+                if ((rc = launch_big_kernel(e, bf, q))) return rc;
+            } else {
+                q.ntiles = ((q.chunk_frames + 7) / 8) * R;
+                const long long cap = (long long)e->sm_count * occ;
+                const int grid = (int)(q.ntiles < cap ? q.ntiles : cap);
+                prof_begin(e);
+                CU(fn(12, &q, grid, smem, e->stream, nullptr));
+                prof_end(e);
+            }
             e->launches += 2;
         }
     }
-    sp::finalize_kernel<<<1, 1024, 0, e->stream>>>(p.fmin, p.fmax, p.fmid, p.nframes, j.range, j.gain, j.plan.sub_r > 1 ? 1 : 0,
-                                                   j.d_gmin, j.d_gmax, j.d_gamp, j.d_stats);
-    e->launches++;
+    return SP_OK;
+}
+
+static int enqueue_end(sp_engine *e, Job &j)
+{
+    Params &p = j.p;
+    sp::finalize_init_kernel<<<1, 1, 0, e->stream>>>((unsigned *)e->mm.p);
+    sp::finalize_kernel<<<(unsigned)((p.nframes + 255) / 256), 256, 0, e->stream>>>(
+        p.fmin, p.fmax, p.fmid, p.nframes, j.range, j.gain, j.plan.sub_r > 1 ? 1 : 0, j.d_gmin, j.d_gmax, j.d_gamp,
+        (unsigned *)e->mm.p, j.d_stats);
+    e->launches += 2;
     CU(cudaGetLastError());
     CU(cudaEventRecord(e->ev1, e->stream));
     return SP_OK;
+}
+
+static int enqueue(sp_engine *e, Job &j)
+{
+    int rc;
+    if ((rc = enqueue_begin(e, j)) || (rc = enqueue_frames(e, j, j.p))) return rc;
+    return enqueue_end(e, j);
+}
+
+static int finish(sp_engine *e, sp_reply *rp);
+
+// ------------------------------------------------------------------ pipelined host-buffer path
+// Host input -> host outputs for a long message: the frames are cut into chunks and three streams
+// overlap the H2D copy of chunk i+1, the render of chunk i and the D2H copy of chunk i-1 (PCIe is
+// full duplex), with two device buffers each for input bytes and image tiles.  Every chunk is a
+// frame-range shard of the SAME message (global stride, global frame indices), so the result is
+// bit-identical to the single-shot path; histograms accumulate across chunks, min / max / gauges
+// are finalised once.  Host memory should be page-locked (sp_host_alloc_pinned) for real overlap.
+static long long pipeline_chunk_frames(const sp_request *rq)
+{
+    const char *env = getenv("SP_PIPE_MB");                  // chunk size in MB; 0 disables the pipeline
+    const long long mb = env ? atoll(env) : 32;
+    if (mb <= 0) return 0;
+    const double in_per_frame = (double)rq->byte_length / (double)rq->width;
+    const double out_per_frame = 4.0 * rq->n;
+    const double per = in_per_frame > out_per_frame ? in_per_frame : out_per_frame;
+    long long ch = (long long)((double)(mb << 20) / per);
+    ch = ch / 8 * 8;
+    if (ch < 64) ch = 64;
+    return (rq->width >= 3 * ch) ? ch : 0;       // short messages: single shot
+}
+
+static int render_pipelined(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, long long ch, double sample_count)
+{
+    const int n = rq->n, sw = sp::sample_width(rq->format);
+    const long long W = rq->width;
+    const bool shard = rq->total_width != 0 || rq->total_byte_length != 0;
+    const long long g_first = shard ? rq->frame_first : 0;                 // global index of local frame 0
+    const long long buf_first = shard ? (long long)rq->buffer_first_sample : 0;
+    const double stride = j.p.stride;
+    if (!e->s_h2d) {
+        CU(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CU(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&e->ev_comp[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming));
+        }
+        CU(cudaEventCreateWithFlags(&e->ev_setup, cudaEventDisableTiming));
+    }
+    int rc;
+    // worst-case chunk input: ch frames at the global stride plus the window-length halo
+    const size_t in_cap = (size_t)(((double)ch * (stride > n ? stride : stride) + 2.0 * n + 64) * sw) + 64;
+    const size_t img_cap = (size_t)4 * (size_t)ch * (size_t)n;
+    for (int i = 0; i < 2; i++)
+        if ((rc = ensure(e, e->pin[i], in_cap)) || (rc = ensure(e, e->pimg[i], img_cap))) return rc;
+    if ((rc = enqueue_begin(e, j))) return rc;
+    CU(cudaEventRecord(e->ev_setup, e->stream));                           // tables / window / LUT uploaded, histograms zeroed
+    CU(cudaStreamWaitEvent(e->s_h2d, e->ev_setup, 0));
+    CU(cudaStreamWaitEvent(e->s_d2h, e->ev_setup, 0));
+    const long long nchunks = (W + ch - 1) / ch;
+    for (long long c = 0; c < nchunks; c++) {
+        const int b = (int)(c & 1);
+        const long long x0 = c * ch, cw = (W - x0 < ch) ? W - x0 : ch;
+        // samples this chunk reads: [pos(x0), pos(x0 + cw - 1) + n), start rounded down to 16 samples
+        long long s0 = (long long)(0.5 + stride * (double)(g_first + x0));
+        long long s1 = (long long)(0.5 + stride * (double)(g_first + x0 + cw - 1)) + n;
+        s0 -= s0 % 16;
+        if (s0 < buf_first) s0 = buf_first;
+        unsigned long long b0 = (unsigned long long)(s0 - buf_first) * sw, b1 = (unsigned long long)(s1 - buf_first) * sw;
+        if (b1 > rq->byte_length || c == nchunks - 1) b1 = rq->byte_length;  // ragged tail bytes travel with the last chunk
+        if (b0 > b1) b0 = b1;
+        if (b1 - b0 + 16 > in_cap) return fail(e, SP_E_RANGE, "internal: pipeline chunk larger than its buffer");
+        // input buffer b is free once the render of chunk c-2 is done
+        if (c >= 2) CU(cudaStreamWaitEvent(e->s_h2d, e->ev_comp[b], 0));
+        CU(cudaMemcpyAsync(e->pin[b].p, (const uint8_t *)rq->buffer + b0, b1 - b0, cudaMemcpyHostToDevice, e->s_h2d));
+        CU(cudaEventRecord(e->ev_in[b], e->s_h2d));
+        // render: needs the input, and image tile b drained by the D2H of chunk c-2
+        CU(cudaStreamWaitEvent(e->stream, e->ev_in[b], 0));
+        if (c >= 2) CU(cudaStreamWaitEvent(e->stream, e->ev_out[b], 0));
+        Params q = j.p;
+        q.buf = (const uint8_t *)e->pin[b].p;
+        q.valid_bytes = b1 - b0;
+        q.sample_base = s0;
+        q.frame_first = g_first + x0;
+        q.nframes = cw;
+        q.chunk_first = 0;
+        q.chunk_frames = cw;
+        q.fmin = j.p.fmin + x0; q.fmax = j.p.fmax + x0; q.fmid = j.p.fmid + x0;
+        q.image = j.d_image ? (uint8_t *)e->pimg[b].p : nullptr;
+        if ((rc = enqueue_frames(e, j, q))) return rc;
+        CU(cudaEventRecord(e->ev_comp[b], e->stream));
+        if (j.d_image) {
+            CU(cudaStreamWaitEvent(e->s_d2h, e->ev_comp[b], 0));
+            if (rq->waterfall)      // rows [W - x0 - cw, W - x0) of the [W][n] image (lib/worker.js:116)
+                CU(cudaMemcpyAsync(rp->image + (size_t)4 * n * (size_t)(W - x0 - cw), e->pimg[b].p, (size_t)4 * n * cw,
+                                   cudaMemcpyDeviceToHost, e->s_d2h));
+            else                    // columns [x0, x0 + cw) of the [n][W] image (lib/worker.js:117)
+                CU(cudaMemcpy2DAsync(rp->image + 4 * x0, (size_t)4 * W, e->pimg[b].p, (size_t)4 * cw, (size_t)4 * cw, (size_t)n,
+                                     cudaMemcpyDeviceToHost, e->s_d2h));
+            CU(cudaEventRecord(e->ev_out[b], e->s_d2h));
+        }
+    }
+    if ((rc = enqueue_end(e, j))) return rc;
+    if (rp->gauge_mins) CU(cudaMemcpyAsync(rp->gauge_mins, j.d_gmin, (size_t)W, cudaMemcpyDeviceToHost, e->stream));
+    if (rp->gauge_maxs) CU(cudaMemcpyAsync(rp->gauge_maxs, j.d_gmax, (size_t)W, cudaMemcpyDeviceToHost, e->stream));
+    if (rp->gauge_amps) CU(cudaMemcpyAsync(rp->gauge_amps, j.d_gamp, (size_t)W, cudaMemcpyDeviceToHost, e->stream));
+    if (rp->cB_hist) CU(cudaMemcpyAsync(rp->cB_hist, j.d_cb, 8 * SP_CB_HIST_SIZE, cudaMemcpyDeviceToHost, e->stream));
+    if (rp->c_hist) CU(cudaMemcpyAsync(rp->c_hist, j.d_c, 8 * (size_t)rq->cmap_len, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->s_d2h));
+    (void)sample_count;
+    return finish(e, rp);
 }
 
 static int finish(sp_engine *e, sp_reply *rp)
@@ -539,8 +772,12 @@ extern "C" int sp_render(sp_engine *e, const sp_request *rq, sp_reply *rp)
 {
     if (!e || !rq || !rp) return fail(e, SP_E_INVAL, "null argument");
     Job j;
+    const bool host_io = !(rq->flags & (SP_F_BUFFER_ON_DEVICE | SP_F_REPLY_ON_DEVICE));
+    const long long ch = (host_io && rq->width > 0 && rq->n > 0 && rq->byte_length > 0) ? pipeline_chunk_frames(rq) : 0;
+    j.pipelined = ch > 0;
     int rc = prepare(e, rq, rp, j, false, nullptr);
     if (rc) return rc;
+    if (j.pipelined) return render_pipelined(e, rq, rp, j, ch, 0.0);
     if ((rc = enqueue(e, j))) return rc;
     const size_t W = (size_t)rq->width;
     if (!(rq->flags & SP_F_REPLY_ON_DEVICE)) {

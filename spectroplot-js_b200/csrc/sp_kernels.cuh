@@ -28,7 +28,8 @@ struct Params {
     long long frame_first;         // global index of local frame 0
     long long nframes;             // frames rendered by this launch (image width in pixels)
     const float *window;           // n_full fp32 coefficients (rounded once from double)
-    const float2 *tw;              // twiddle table exp(-2 pi j i / n_kernel), i < n_kernel
+    const float2 *twA;             // pass-A twiddles [15][T]:  W_N^{t*k},      k = 1..15 (N = kernel size, T = N/16)
+    const float2 *twB;             // pass-B twiddles [15][RL]: W_{N/16}^{b*k}, k = 1..15 (3-pass sizes only)
     // dB / colour mapping
     float c0, c1;                  // d0 = c1 * log2(|X|^2) + c0
     float gn, gc, cmaxf;           // gray = trunc(0.5 + clamp(gn * d0 + gc, 0, cmax))
@@ -74,10 +75,26 @@ template <int LOG2N> struct Cfg {
 };
 
 constexpr int CB_BINS = 1000;     // lib/worker.js:41
+// Shared-memory dB histogram is indexed by the RAW saturating conversion r = u32(2.5 - 10*d0):
+//   r == 0            d0 > +0.15 dB: the reference's negative index, not counted   (lib/worker.js:106)
+//   r == 1, 2         bin 0        (~~ truncates toward zero: (-1, 1) -> 0)
+//   3 <= r <= 1001    bin r - 2
+//   1002 <= r < CAP   bin 999      (cBabs >= 1000)
+//   r == CAP          d0 == -inf (|X|^2 == 0): ~~(+Infinity) == 0 -> bin 0
+// so the per-pixel work is FFMA + F2I + IMNMX + ATOMS with no compare / select; the mapping is
+// applied once per CTA when the counters are flushed.  The engine rejects block_norm so small that a
+// finite d0 could reach CAP (10*log10(block_norm) < -75 dB).
+constexpr int CB_RAW_CAP = 3071;
+constexpr int CB_RAW = CB_RAW_CAP + 1;
 
-__host__ __device__ inline size_t main_smem_bytes(int smem_x_float2, int cmap_len)
+__host__ __device__ inline size_t main_smem_bytes(int smem_x_float2, int cmap_len, int twb_float2)
 {
-    return (size_t)smem_x_float2 * 8 + (size_t)(CB_BINS + cmap_len) * 4 + (size_t)cmap_len * 4 + 64 * 8;
+    return (size_t)smem_x_float2 * 8 + (size_t)CB_RAW * 4 + (size_t)cmap_len * 8 + 64 * 8 + (size_t)twb_float2 * 8;
+}
+
+__device__ __forceinline__ int cb_bin_of_raw(int r)
+{
+    return r == 0 ? -1 : (r <= 2 ? 0 : (r <= 1001 ? r - 2 : (r < CB_RAW_CAP ? CB_BINS - 1 : 0)));
 }
 
 // first output bin of butterfly j of thread t in the last pass (bin = kbase + kstep * k)
@@ -99,6 +116,26 @@ __device__ __forceinline__ float ord2f(unsigned u)
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
+// shared-memory counters -> 64-bit global histograms (raw dB index mapped to the reference's bins)
+__device__ __forceinline__ void flush_hist(unsigned *s_cb, uint2 *s_col, const Params &p, int tid, int nthreads, bool clear)
+{
+    for (int i = tid; i < CB_RAW; i += nthreads) {
+        const unsigned c = s_cb[i];
+        if (c) {
+            const int b = cb_bin_of_raw(i);
+            if (b >= 0) atomicAdd(&p.cb_hist[b], (unsigned long long)c);
+            if (clear) s_cb[i] = 0;
+        }
+    }
+    for (int i = tid; i < p.cmap_len; i += nthreads) {
+        const unsigned c = s_col[i].y;
+        if (c) {
+            atomicAdd(&p.c_hist[i], (unsigned long long)c);
+            if (clear) s_col[i].y = 0;
+        }
+    }
+}
+
 template <int LOG2N, int FMT>
 __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
 {
@@ -107,10 +144,10 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
     constexpr int kstep = C::PASSES == 1 ? 1 : (C::PASSES == 2 ? 16 : 256);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *xbuf = reinterpret_cast<float2 *>(smem_raw);
-    unsigned *s_cb = reinterpret_cast<unsigned *>(xbuf + C::SMEM_X);
-    unsigned *s_c = s_cb + CB_BINS;
-    unsigned *s_lut = s_c + p.cmap_len;
-    float2 *s_mm = reinterpret_cast<float2 *>(s_lut + p.cmap_len);   // [64] per-warp min/max partials
+    unsigned *s_cb = reinterpret_cast<unsigned *>(xbuf + C::SMEM_X);           // [CB_RAW] raw dB histogram
+    uint2 *s_col = reinterpret_cast<uint2 *>(s_cb + CB_RAW);                    // [cmap_len] {RGBA, count}
+    float2 *s_mm = reinterpret_cast<float2 *>(s_col + p.cmap_len);              // [64] per-warp min/max partials
+    float2 *s_twB = s_mm + 64;                                                  // [15][RL] pass-B twiddles
 
     const int tid = threadIdx.x;
     const int slot = tid / T;
@@ -119,8 +156,14 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
     float2 *bufB = bufA + C::SIZE_A;
     (void)bufA; (void)bufB;
 
-    for (int i = tid; i < CB_BINS + p.cmap_len; i += C::THREADS) s_cb[i] = 0;
-    for (int i = tid; i < p.cmap_len; i += C::THREADS) s_lut[i] = p.lut[i];
+    for (int i = tid; i < CB_RAW; i += C::THREADS) s_cb[i] = 0;
+    for (int i = tid; i < p.cmap_len; i += C::THREADS) s_col[i] = make_uint2(p.lut[i], 0u);
+    if constexpr (C::PASSES == 3)
+        for (int i = tid; i < 15 * C::RL; i += C::THREADS) s_twB[i] = p.twB[i];
+    const unsigned cmax_u = (unsigned)(p.cmap_len - 1);
+    const float gc5 = p.gc + 0.5f;
+    const float l2c_k = -10.0f * p.c1, l2c_k0 = fmaf(-10.0f, p.c0, 2.5f);       // raw cB index = l2c_k * log2|X|^2 + l2c_k0
+    const float l2c_g = p.gn * p.c1, l2c_g0 = fmaf(p.gn, p.c0, gc5);             // colour index  = l2c_g * log2|X|^2 + l2c_g0
 
     const bool sub = p.sub_r > 1;
     const int nfull = p.n_full;
@@ -168,12 +211,17 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
                     (unsigned long long)(p0 + N) * (unsigned)sample_width(FMT == FMT_RUNTIME ? p.format : FMT) <= p.valid_bytes;
                 if (inside) {
 #pragma unroll
-                    for (int a = 0; a < P; a++) v[a] = decode_fast<FMT>(p.buf, p0 + T * a + t, p.format);
-                } else {
+                    for (int a = 0; a < P; a++) v[a] = decode_raw<FMT>(p.buf, p0 + T * a + t, p.format);
+                } else {                                       // slow path: frames touching a ragged buffer end
+                    const float inv = 1.0f / raw_scale<FMT>();
 #pragma unroll
-                    for (int a = 0; a < P; a++) v[a] = decode_checked(p.buf, p0 + T * a + t, p.format, p.valid_bytes);
+                    for (int a = 0; a < P; a++) {
+                        v[a] = decode_checked(p.buf, p0 + T * a + t, p.format, p.valid_bytes);
+                        v[a].x *= inv; v[a].y *= inv;
+                    }
                 }
-                if (t == 0 && active) p.fmid[xl] = v[P / 2];   // raw sample at p0 + n/2 (lib/worker.js:131-133)
+                // raw sample at p0 + n/2 (lib/worker.js:131-133); the power-of-two scale is exact
+                if (t == 0 && active) p.fmid[xl] = make_float2(v[P / 2].x * raw_scale<FMT>(), v[P / 2].y * raw_scale<FMT>());
 #pragma unroll
                 for (int a = 0; a < P; a++) { v[a].x *= win[a]; v[a].y *= win[a]; }
             }
@@ -181,10 +229,8 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
             // ---------------- FFT pass A: radix P over the slowest input digit ----------------
             dft<P>(v);
             if constexpr (C::PASSES >= 2) {
-                {
-                    const float2 w1 = p.tw[t], w2 = p.tw[2 * t], w4 = p.tw[4 * t], w8 = p.tw[8 * t];
-                    twiddle16(v, w1, w2, w4, w8);             // W_N^{t*k0}
-                }
+#pragma unroll
+                for (int k = 1; k < 16; k++) v[k] = cmul(v[k], __ldg(p.twA + (k - 1) * T + t));   // W_N^{t*k}
 #pragma unroll
                 for (int k = 0; k < 16; k++) bufA[k * C::PITCH_A + t] = v[k];
                 __syncthreads();
@@ -196,11 +242,8 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
 #pragma unroll
                 for (int a = 0; a < 16; a++) v[a] = bufA[k0 * C::PITCH_A + R2 * a + b1];
                 dft<16>(v);
-                {
-                    const int e = 16 * b1;                    // W_{N/16}^{b1*k1} = W_N^{16*b1*k1}
-                    const float2 w1 = p.tw[e], w2 = p.tw[2 * e], w4 = p.tw[4 * e], w8 = p.tw[8 * e];
-                    twiddle16(v, w1, w2, w4, w8);
-                }
+#pragma unroll
+                for (int k = 1; k < 16; k++) v[k] = cmul(v[k], s_twB[(k - 1) * R2 + b1]);         // W_{N/16}^{b1*k}
 #pragma unroll
                 for (int k = 0; k < 16; k++) bufB[k0 * C::PITCH_B + k * C::P1 + b1] = v[k];
                 __syncthreads();
@@ -258,41 +301,60 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
             }
 
             // ---------------- per-bin epilogue (lib/worker.js:85-122) ----------------
-            float mn = 0.0f, mx = -200.0f;                     // lib/worker.js:82-83
+            // min / max are tracked on |X|^2 (log2 and the FMA are monotone), converted once per thread
+            float amin = __int_as_float(0x7f800000), amax = 0.0f;
+            float vabs[P / 2 > 0 ? P / 2 : 1];
 #pragma unroll
-            for (int j = 0; j < C::NB; j++)
+            for (int i = 0; i < P; i++) {
+                const float abs2 = fmaf(v[i].x, v[i].x, v[i].y * v[i].y);
+                if (i & 1) {                                 // 3-input min / max (NaN never wins, like `<` in JS)
+                    const float prev = vabs[i >> 1];
+                    amin = fmin3(amin, prev, abs2);
+                    amax = fmax3(amax, prev, abs2);
+                } else vabs[i >> 1] = abs2;
+                const float l2 = fast_log2(abs2);                              // dBfs - gain = c1*l2 + c0 (lib/worker.js:93)
+                // saturating float->uint conversions do the clamping: negative / NaN -> 0, +inf -> max
+                const float kf = fmaf(l2, l2c_k, l2c_k0);
+                unsigned cr = min(__float2uint_rz(kf), (unsigned)CB_RAW_CAP);                             // :105-106
+                if constexpr (FMT == CF32 || FMT == CF64 || FMT == FMT_RUNTIME)
+                    if (!(fabsf(kf) <= 3.0e9f)) cr = 1;     // NaN / -inf (only float input can do this): ~~v == 0 -> bin 0
+                const unsigned g = min(__float2uint_rz(fmaf(l2, l2c_g, l2c_g0)), cmax_u);                 // :111-112
+                if (active) {
+                    atomicAdd(&s_cb[cr], 1u);
+                    atomicAdd(&s_col[g].y, 1u);                             // :113
+                }
+                // byte f of (ghi:glo) = colour index of frame f of this slot
+                glo[i] = __funnelshift_r(glo[i], ghi[i], 8);
+                ghi[i] = __funnelshift_r(ghi[i], g, 8);
+            }
+            float mn = fminf(0.0f, fmaf(fast_log2(amin), p.c1, p.c0));        // lib/worker.js:82,102
+            float mx = fmaxf(-200.0f, fmaf(fast_log2(amax), p.c1, p.c0));     // lib/worker.js:83,103
+
+            // slow outputs (uniform branch, once per frame): per-pixel stores and the dB tap
+            if ((direct | (p.db_out != nullptr)) && active) {
+#pragma unroll 1
+                for (int j = 0; j < C::NB; j++)
+#pragma unroll 1
+                    for (int k = 0; k < C::RL; k++) {
+                        const int i = j * C::RL + k;
+                        float2 vi = v[0];
 #pragma unroll
-                for (int k = 0; k < C::RL; k++) {
-                    const int i = j * C::RL + k;
-                    const float abs2 = fmaf(v[i].x, v[i].x, v[i].y * v[i].y);
-                    const float d0 = fmaf(__log2f(abs2), p.c1, p.c0);        // dBfs - gain
-                    mn = fminf(mn, d0);
-                    mx = fmaxf(mx, d0);
-                    int cb = js_trunc(fmaf(d0, -10.0f, 0.5f));                // lib/worker.js:105
-                    cb = min(cb, CB_BINS - 1);
-                    const float gf = fminf(fmaxf(fmaf(d0, p.gn, p.gc), 0.0f), p.cmaxf);
-                    const int g = __float2int_rz(gf + 0.5f);                  // lib/worker.js:112
-                    if (active) {
-                        if (cb >= 0) atomicAdd(&s_cb[cb], 1u);               // lib/worker.js:106
-                        atomicAdd(&s_c[g], 1u);                              // lib/worker.js:113
-                    }
-                    // byte f of (ghi:glo) = colour index of frame f of this slot
-                    glo[i] = __funnelshift_r(glo[i], ghi[i], 8);
-                    ghi[i] = __funnelshift_r(ghi[i], (unsigned)g, 8);
-                    if (direct | (p.db_out != nullptr)) {
-                        const int bin = sub ? k0sub + sub_r * (kbase[j] + kstep * k) : kbase[j] + kstep * k;
-                        if (active) {
-                            if (p.db_out) p.db_out[(size_t)xl * nfull + bin] = d0;
-                            if (direct) {
-                                const int y = (nfull / 2 - bin) & (nfull - 1);                 // lib/worker.js:90
-                                const size_t px = p.waterfall
-                                    ? (size_t)nfull * (size_t)(p.nframes - 1 - xl) + (size_t)(nfull - 1 - y)   // :116
-                                    : (size_t)xl + (size_t)p.nframes * (size_t)y;                              // :117
-                                reinterpret_cast<uint32_t *>(p.image)[px] = s_lut[g];
-                            }
+                        for (int q = 0; q < P; q++) if (q == i) vi = v[q];   // register select, no local memory
+                        const int kb = kbase_of<C>(t, j);
+                        const int bin = sub ? k0sub + sub_r * (kb + kstep * k) : kb + kstep * k;
+                        const float abs2 = fmaf(vi.x, vi.x, vi.y * vi.y);
+                        const float d0 = fmaf(fast_log2(abs2), p.c1, p.c0);
+                        const unsigned gi = min(__float2uint_rz(fmaf(fast_log2(abs2), l2c_g, l2c_g0)), cmax_u);   // (cmap_len may exceed 256)
+                        if (p.db_out) p.db_out[(size_t)xl * nfull + bin] = d0;
+                        if (direct) {
+                            const int y = (nfull / 2 - bin) & (nfull - 1);                     // lib/worker.js:90
+                            const size_t px = p.waterfall
+                                ? (size_t)nfull * (size_t)(p.nframes - 1 - xl) + (size_t)(nfull - 1 - y)   // :116
+                                : (size_t)xl + (size_t)p.nframes * (size_t)y;                              // :117
+                            reinterpret_cast<uint32_t *>(p.image)[px] = s_col[gi].x;
                         }
                     }
-                }
+            }
 
             // ---------------- per-frame min / max (lib/worker.js:102-103) ----------------
 #pragma unroll
@@ -325,12 +387,12 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
                     const int y = (nfull / 2 - bin) & (nfull - 1);
                     uint32_t *row = reinterpret_cast<uint32_t *>(p.image) + (size_t)p.nframes * (size_t)y + x0;
                     uint4 a, b;
-                    a.x = s_lut[glo[i] & 255]; a.y = s_lut[(glo[i] >> 8) & 255];
-                    a.z = s_lut[(glo[i] >> 16) & 255]; a.w = s_lut[glo[i] >> 24];
+                    a.x = s_col[glo[i] & 255].x; a.y = s_col[(glo[i] >> 8) & 255].x;
+                    a.z = s_col[(glo[i] >> 16) & 255].x; a.w = s_col[glo[i] >> 24].x;
                     reinterpret_cast<uint4 *>(row)[0] = a;
                     if (full8) {                               // else nframes % 4 == 0: exactly 4 frames left
-                        b.x = s_lut[ghi[i] & 255]; b.y = s_lut[(ghi[i] >> 8) & 255];
-                        b.z = s_lut[(ghi[i] >> 16) & 255]; b.w = s_lut[ghi[i] >> 24];
+                        b.x = s_col[ghi[i] & 255].x; b.y = s_col[(ghi[i] >> 8) & 255].x;
+                        b.z = s_col[(ghi[i] >> 16) & 255].x; b.w = s_col[ghi[i] >> 24].x;
                         reinterpret_cast<uint4 *>(row)[1] = b;
                     }
                 }
@@ -362,23 +424,14 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
         px_since_flush += (unsigned long long)C::TILE * N;
         if (px_since_flush >= (1ull << 31)) {
             __syncthreads();
-            for (int i = tid; i < CB_BINS + p.cmap_len; i += C::THREADS) {
-                const unsigned c = s_cb[i];
-                if (c) {
-                    atomicAdd(i < CB_BINS ? &p.cb_hist[i] : &p.c_hist[i - CB_BINS], (unsigned long long)c);
-                    s_cb[i] = 0;
-                }
-            }
+            flush_hist(s_cb, s_col, p, tid, C::THREADS, true);
             px_since_flush = 0;
             __syncthreads();
         }
     } // tiles
 
     __syncthreads();
-    for (int i = tid; i < CB_BINS + p.cmap_len; i += C::THREADS) {
-        const unsigned c = s_cb[i];
-        if (c) atomicAdd(i < CB_BINS ? &p.cb_hist[i] : &p.c_hist[i - CB_BINS], (unsigned long long)c);
-    }
+    flush_hist(s_cb, s_col, p, tid, C::THREADS, false);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -403,12 +456,16 @@ __global__ void __launch_bounds__(256) prepass_kernel(const Params p, float2 *__
     float2 v[R];
     if (inside) {
 #pragma unroll
-        for (int a = 0; a < R; a++) v[a] = decode_fast<FMT>(p.buf, p0 + NS * a + b, p.format);
+        for (int a = 0; a < R; a++) v[a] = decode_raw<FMT>(p.buf, p0 + NS * a + b, p.format);
     } else {
+        const float inv = 1.0f / raw_scale<FMT>();
 #pragma unroll
-        for (int a = 0; a < R; a++) v[a] = decode_checked(p.buf, p0 + NS * a + b, p.format, p.valid_bytes);
+        for (int a = 0; a < R; a++) {
+            v[a] = decode_checked(p.buf, p0 + NS * a + b, p.format, p.valid_bytes);
+            v[a].x *= inv; v[a].y *= inv;
+        }
     }
-    if (b == 0) p.fmid[xl] = v[R / 2];             // sample p0 + n/2
+    if (b == 0) p.fmid[xl] = make_float2(v[R / 2].x * raw_scale<FMT>(), v[R / 2].y * raw_scale<FMT>());   // sample p0 + n/2
 #pragma unroll
     for (int a = 0; a < R; a++) { const float w = p.window[NS * a + b]; v[a].x *= w; v[a].y *= w; }
     dft<R>(v);

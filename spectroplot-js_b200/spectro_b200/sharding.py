@@ -43,3 +43,14 @@ def merge_stats(parts):
     mn = min([0.0] + [p["dBfs_min"] for p in parts])
     mx = max([-200.0] + [p["dBfs_max"] for p in parts])
     return dict(cB_hist=cB, c_hist=c, dBfs_min=mn, dBfs_max=mx)
+
+
+def allreduce_stats(dist, hist, minmax):
+    """The one exchange step of the multi-GPU path: `hist` (int64 tensor, cB_hist | c_hist) is summed,
+    `minmax` (float64 tensor [dBfs_min, dBfs_max]) is folded, in place, over all ranks.  Works on the
+    NCCL backend (device tensors, bench.py) and on gloo (CPU tensors, tests)."""
+    dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+    minmax[1].neg_()
+    dist.all_reduce(minmax, op=dist.ReduceOp.MIN)      # min(min) and -max(max) in one MIN reduction
+    minmax[1].neg_()
+    return hist, minmax

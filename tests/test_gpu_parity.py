@@ -290,3 +290,27 @@ def test_properties_at_scale(engine):
         o = O.render(fb, "CS16", n, 2, w, 1 / wt, 6, 30, CM256, taps=True)
         d_ = g[x].astype(int) - o.gray[0].astype(int)
         assert np.abs(d_).max() <= 1 and (d_ != 0).sum() <= 8
+
+
+# ------------------------------------------------------------------ pipelined host path == single shot
+@pytest.mark.parametrize("case", [("CS16", 1024, 1000, 700, False), ("CU8", 256, 4001, 300, False),
+                                  ("CS16", 4096, 800, 4096, False), ("CF32", 512, 1500, 512, True),
+                                  ("CF32", 8192, 100, 5000, False)])
+def test_pipelined_host_path_is_bit_identical(engine, case, monkeypatch):
+    """Long host-buffer messages are streamed in frame-range chunks over three CUDA streams
+    (H2D / render / D2H overlap); the chunks are shards of the same message, so nothing may change."""
+    fmt, n, width, hop, wf = case
+    S = hop * (width - 1) + n + 3
+    buf = O.synth(fmt, 0, S, S, 0x5EC79000 + n).tobytes()
+    w, wt = O.window("hann", n)
+    monkeypatch.setenv("SP_PIPE_MB", "0")
+    one = engine.render(buf, fmt, n, width, w, 1 / wt, 6, 30, CM256, waterfall=wf)
+    monkeypatch.setenv("SP_PIPE_MB", "1")
+    pin = __import__("spectro_b200").PinnedBuffer(len(buf))
+    pin.array[:] = np.frombuffer(buf, np.uint8)
+    pipe = engine.render(pin.array, fmt, n, width, w, 1 / wt, 6, 30, CM256, waterfall=wf)
+    for k in ("image", "cB_hist", "c_hist", "gauge_mins", "gauge_maxs", "gauge_amps"):
+        assert np.array_equal(one[k], pipe[k]), k
+    assert one["dBfs_min"] == pipe["dBfs_min"] and one["dBfs_max"] == pipe["dBfs_max"]
+    assert pipe["kernel_launches"] > one["kernel_launches"]          # it really was chunked
+    pin.free()
