@@ -297,12 +297,16 @@ extern "C" const char *sp_kernel_plan(sp_engine *e, int format, int n, int chann
 {
     if (!e) return "";
     const int l = ilog2_exact(n);
-    char buf[256];
+    char buf[384];
     if (l < 3 || l > 16 || format < 0 || format >= SP_FORMAT_COUNT) { e->plan = "unsupported"; return e->plan.c_str(); }
     Plan pl = make_plan(l);
     snprintf(buf, sizeof buf, "%s%srender_kernel<N=%d,%s> tile=%d frames smem_x=%d B%s", pl.sub_r > 1 ? "prepass_kernel<R=" : "",
              pl.sub_r > 1 ? (std::to_string(pl.sub_r) + "> + ").c_str() : "", 1 << pl.log2k,
              specialised(format) ? k_names[format] : "runtime-format", pl.tile, pl.smem_x * 8, channel_mode ? " +splitreal" : "");
+    if (pl.log2k == 12 && !channel_mode && !getenv("SP_NO_BIG")) {
+        const size_t l = strlen(buf);
+        snprintf(buf + l, sizeof buf - l, " | spectrogram fast path: render_big_kernel<slots=2,frames=8> (TMA-staged input)");
+    }
     e->plan = buf;
     return e->plan.c_str();
 }
