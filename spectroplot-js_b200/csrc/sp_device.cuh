@@ -2,7 +2,8 @@
 //
 //  * sample decoders: bit-exact fp32 versions of SampleView.sampleI/Q
 //    (reference lib/samples.js:313-400), i.e. gpu == fround(reference double)
-//  * register-resident radix-2/4/8/16 butterflies used by the shared-memory FFT
+//  * register-resident radix-2/4/8/16 butterflies used by the shared-memory FFT, issued as
+//    packed-fp32 instructions (FADD2 / FMUL2 / FFMA2)
 //    (replaces the radix-2 transform of reference lib/fft_nayuki.js:54-86)
 //  * JS number helpers (`~~v`)
 #pragma once
@@ -176,8 +177,14 @@ __device__ __forceinline__ float2 decode_raw(const uint8_t *__restrict__ buf, lo
         int b0 = p[0], b1 = p[1], b2 = p[2];
         return make_float2((float)sext(((b1 & 15) << 8) | b0, 12), (float)sext((b2 << 4) | (b1 >> 4), 12));
     } else if constexpr (FMT == CS16) {
+        // two I2F.S16 reading the low / high half of the loaded word directly (no shift)
         unsigned v = *reinterpret_cast<const unsigned *>(buf + 4 * s);
-        return make_float2((float)(int)(short)(v & 0xffff), (float)((int)v >> 16));
+        short lo, hi;
+        float2 r;
+        asm("mov.b32 {%0, %1}, %2;" : "=h"(lo), "=h"(hi) : "r"(v));
+        asm("cvt.rn.f32.s16 %0, %1;" : "=f"(r.x) : "h"(lo));
+        asm("cvt.rn.f32.s16 %0, %1;" : "=f"(r.y) : "h"(hi));
+        return r;
     } else if constexpr (FMT == CU16) {
         unsigned v = *reinterpret_cast<const unsigned *>(buf + 4 * s);
         return make_float2((float)(2 * (int)(v & 0xffff) - 65535), (float)(2 * (int)(v >> 16) - 65535));
@@ -267,98 +274,111 @@ static __device__ __noinline__ float2 decode_checked(const uint8_t *__restrict__
 }
 
 // ------------------------------------------------------------------ complex helpers
+// A complex value lives in one aligned 64-bit register pair (re = low word, im = high word) and
+// all FFT arithmetic is issued as Blackwell packed-fp32 instructions (PTX add/sub/mul/fma .f32x2,
+// SASS FADD2 / FMUL2 / FFMA2): one issue slot per complex add, two per complex multiply.  The
+// pack / unpack `mov.b64` below never reach SASS: ptxas folds them into the operand modifiers of
+// the packed instructions (scalar broadcast `R.F32`, swapped halves `R.F32x2.LO_HI`, per-half
+// negation `.NP`), so multiplication by +-j is free and a twiddle needs no duplicated registers.
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 w)
-{
-    return make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
-}
-// multiply by -j  (W4^1 of the forward transform)
-__device__ __forceinline__ float2 mul_mj(float2 a) { return make_float2(a.y, -a.x); }
+struct cf { unsigned long long u; };
 
-// forward DFT-2 / DFT-4 on registers: y[k] = sum_n x[n] * exp(-2 pi j n k / R)
-__device__ __forceinline__ void dft2(float2 &a, float2 &b)
+__device__ __forceinline__ cf cpk(float lo, float hi) { cf r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.u) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ cf cpk(float2 a) { return cpk(a.x, a.y); }
+__device__ __forceinline__ float2 cun(cf v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v.u)); return r; }
+__device__ __forceinline__ float cre(cf v) { return cun(v).x; }
+__device__ __forceinline__ float cim(cf v) { return cun(v).y; }
+__device__ __forceinline__ cf cld(const float2 *p) { cf r; r.u = *reinterpret_cast<const unsigned long long *>(p); return r; }
+__device__ __forceinline__ void cst(float2 *p, cf v) { *reinterpret_cast<unsigned long long *>(p) = v.u; }
+
+__device__ __forceinline__ cf cadd(cf a, cf b) { cf r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.u) : "l"(a.u), "l"(b.u)); return r; }
+__device__ __forceinline__ cf csub(cf a, cf b) { cf r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.u) : "l"(a.u), "l"(b.u)); return r; }
+__device__ __forceinline__ cf cmul2(cf a, cf b) { cf r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.u) : "l"(a.u), "l"(b.u)); return r; }
+__device__ __forceinline__ cf cfma2(cf a, cf b, cf c) { cf r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.u) : "l"(a.u), "l"(b.u), "l"(c.u)); return r; }
+// real scale (window coefficient, 1/sqrt2, ...): FMUL2 with a broadcast scalar
+__device__ __forceinline__ cf cscale(cf a, float s) { return cmul2(a, cpk(s, s)); }
+// a * (w.x + j w.y): FMUL2 + FFMA2
+__device__ __forceinline__ cf cmul(cf a, float2 w)
 {
-    float2 t = a; a = cadd(t, b); b = csub(t, b);
+    const float2 f = cun(a);
+    return cfma2(cpk(f.y, f.x), cpk(-w.y, w.y), cmul2(a, cpk(w.x, w.x)));
 }
-__device__ __forceinline__ void dft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3)
-{
-    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_mj(csub(a1, a3));
-    a0 = cadd(t0, t2); a2 = csub(t0, t2);
-    a1 = cadd(t1, t3); a3 = csub(t1, t3);
-}
+// multiply by -j (W4^1 of the forward transform) / by +j: operand swizzles, no instruction
+__device__ __forceinline__ cf mul_mj(cf a) { const float2 f = cun(a); return cpk(f.y, -f.x); }
+__device__ __forceinline__ cf mul_pj(cf a) { const float2 f = cun(a); return cpk(-f.y, f.x); }
 
 #define SP_SQRT1_2 0.70710678118654752440f
 #define SP_COS_PI_8 0.92387953251128675613f
 #define SP_SIN_PI_8 0.38268343236508977173f
 
+// a * W8^1 = (1 - j)/sqrt2 * a   and   a * W8^3 = -(1 + j)/sqrt2 * a : FADD2 + FMUL2
+__device__ __forceinline__ cf mul_w8_1(cf a) { return cscale(cadd(a, mul_mj(a)), SP_SQRT1_2); }
+__device__ __forceinline__ cf mul_w8_3(cf a) { return cscale(cadd(a, mul_pj(a)), -SP_SQRT1_2); }
+
+// forward DFT-2 / DFT-4 on registers: y[k] = sum_n x[n] * exp(-2 pi j n k / R)
+__device__ __forceinline__ void dft2(cf &a, cf &b)
+{
+    cf t = a; a = cadd(t, b); b = csub(t, b);
+}
+__device__ __forceinline__ void dft4(cf &a0, cf &a1, cf &a2, cf &a3)
+{
+    cf t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_mj(csub(a1, a3));
+    a0 = cadd(t0, t2); a2 = csub(t0, t2);
+    a1 = cadd(t1, t3); a3 = csub(t1, t3);
+}
+
 // in place, natural order in -> natural order out
-template <int R> __device__ __forceinline__ void dft(float2 (&v)[R]);
+template <int R> __device__ __forceinline__ void dft(cf (&v)[R]);
 
-template <> __device__ __forceinline__ void dft<1>(float2 (&)[1]) {}
-template <> __device__ __forceinline__ void dft<2>(float2 (&v)[2]) { dft2(v[0], v[1]); }
-template <> __device__ __forceinline__ void dft<4>(float2 (&v)[4]) { dft4(v[0], v[1], v[2], v[3]); }
+template <> __device__ __forceinline__ void dft<1>(cf (&)[1]) {}
+template <> __device__ __forceinline__ void dft<2>(cf (&v)[2]) { dft2(v[0], v[1]); }
+template <> __device__ __forceinline__ void dft<4>(cf (&v)[4]) { dft4(v[0], v[1], v[2], v[3]); }
 
-template <> __device__ __forceinline__ void dft<8>(float2 (&v)[8])
+template <> __device__ __forceinline__ void dft<8>(cf (&v)[8])
 {
     // n = 4*n1 + n0, k = k0 + 2*k1 :  W8^{nk} = W2^{n1 k0} * W8^{n0 k0} * W4^{n0 k1}
 #pragma unroll
     for (int n0 = 0; n0 < 4; n0++) dft2(v[n0], v[4 + n0]);       // v[n0] : k0 = 0, v[4+n0] : k0 = 1
     // k0 = 1 row times W8^{n0}
-    {
-        float2 a = v[5]; v[5] = make_float2(SP_SQRT1_2 * (a.x + a.y), SP_SQRT1_2 * (a.y - a.x));   // W8^1
-        v[6] = mul_mj(v[6]);                                                                        // W8^2
-        a = v[7]; v[7] = make_float2(SP_SQRT1_2 * (a.y - a.x), -SP_SQRT1_2 * (a.x + a.y));         // W8^3
-    }
+    v[5] = mul_w8_1(v[5]);
+    v[6] = mul_mj(v[6]);
+    v[7] = mul_w8_3(v[7]);
     dft4(v[0], v[1], v[2], v[3]);   // k0 = 0 : outputs k = 0,2,4,6
     dft4(v[4], v[5], v[6], v[7]);   // k0 = 1 : outputs k = 1,3,5,7
-    float2 y[8];
+    cf y[8];
 #pragma unroll
     for (int k1 = 0; k1 < 4; k1++) { y[2 * k1] = v[k1]; y[2 * k1 + 1] = v[4 + k1]; }
 #pragma unroll
     for (int i = 0; i < 8; i++) v[i] = y[i];
 }
 
-template <> __device__ __forceinline__ void dft<16>(float2 (&v)[16])
+template <> __device__ __forceinline__ void dft<16>(cf (&v)[16])
 {
     // n = 4*n1 + n0, k = k0 + 4*k1 :  W16^{nk} = W4^{n1 k0} * W16^{n0 k0} * W4^{n0 k1}
 #pragma unroll
     for (int n0 = 0; n0 < 4; n0++) dft4(v[n0], v[4 + n0], v[8 + n0], v[12 + n0]);   // v[4*k0 + n0]
     // twiddles W16^{n0*k0}
     {
-        const float C = SP_COS_PI_8, S = SP_SIN_PI_8, H = SP_SQRT1_2;
-        float2 a;
+        const float C = SP_COS_PI_8, S = SP_SIN_PI_8;
         v[5] = cmul(v[5], make_float2(C, -S));                                  // k0=1,n0=1 : W16^1
-        a = v[6]; v[6] = make_float2(H * (a.x + a.y), H * (a.y - a.x));         // k0=1,n0=2 : W16^2
+        v[6] = mul_w8_1(v[6]);                                                  // k0=1,n0=2 : W16^2
         v[7] = cmul(v[7], make_float2(S, -C));                                  // k0=1,n0=3 : W16^3
-        a = v[9]; v[9] = make_float2(H * (a.x + a.y), H * (a.y - a.x));         // k0=2,n0=1 : W16^2
+        v[9] = mul_w8_1(v[9]);                                                  // k0=2,n0=1 : W16^2
         v[10] = mul_mj(v[10]);                                                  // k0=2,n0=2 : W16^4
-        a = v[11]; v[11] = make_float2(H * (a.y - a.x), -H * (a.x + a.y));      // k0=2,n0=3 : W16^6
+        v[11] = mul_w8_3(v[11]);                                                // k0=2,n0=3 : W16^6
         v[13] = cmul(v[13], make_float2(S, -C));                                // k0=3,n0=1 : W16^3
-        a = v[14]; v[14] = make_float2(H * (a.y - a.x), -H * (a.x + a.y));      // k0=3,n0=2 : W16^6
+        v[14] = mul_w8_3(v[14]);                                                // k0=3,n0=2 : W16^6
         v[15] = cmul(v[15], make_float2(-C, S));                                // k0=3,n0=3 : W16^9
     }
 #pragma unroll
     for (int k0 = 0; k0 < 4; k0++) dft4(v[4 * k0], v[4 * k0 + 1], v[4 * k0 + 2], v[4 * k0 + 3]);  // -> k1
-    float2 y[16];
+    cf y[16];
 #pragma unroll
     for (int k0 = 0; k0 < 4; k0++)
 #pragma unroll
         for (int k1 = 0; k1 < 4; k1++) y[k0 + 4 * k1] = v[4 * k0 + k1];
 #pragma unroll
     for (int i = 0; i < 16; i++) v[i] = y[i];
-}
-
-// v[k] *= w^k for k = 1..15, given w^1, w^2, w^4, w^8 (11 complex products, depth <= 3)
-__device__ __forceinline__ void twiddle16(float2 (&v)[16], float2 w1, float2 w2, float2 w4, float2 w8)
-{
-    float2 w3 = cmul(w1, w2), w5 = cmul(w1, w4), w6 = cmul(w2, w4), w7 = cmul(w3, w4);
-    v[1] = cmul(v[1], w1);  v[2] = cmul(v[2], w2);  v[3] = cmul(v[3], w3);  v[4] = cmul(v[4], w4);
-    v[5] = cmul(v[5], w5);  v[6] = cmul(v[6], w6);  v[7] = cmul(v[7], w7);  v[8] = cmul(v[8], w8);
-    v[9] = cmul(v[9], cmul(w1, w8));   v[10] = cmul(v[10], cmul(w2, w8)); v[11] = cmul(v[11], cmul(w3, w8));
-    v[12] = cmul(v[12], cmul(w4, w8)); v[13] = cmul(v[13], cmul(w5, w8)); v[14] = cmul(v[14], cmul(w6, w8));
-    v[15] = cmul(v[15], cmul(w7, w8));
 }
 
 } // namespace sp

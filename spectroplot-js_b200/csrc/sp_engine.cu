@@ -5,7 +5,7 @@
 // No CPU fallback exists: without an sm_100 device sp_create fails with SP_E_NO_DEVICE.
 #include "../../include/spectro_b200.h"
 #include "sp_aux_kernels.cuh"
-#include "sp_kernel_big.cuh"
+#include "sp_kernel_fast.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -23,13 +23,13 @@ using sp::Params;
 #define SP_DECL(tag)                                                                                             \
     extern "C" cudaError_t sp_rl_##tag(int, const Params *, int, size_t, cudaStream_t, int *) __attribute__((weak)); \
     extern "C" cudaError_t sp_pl_##tag(int, const Params *, float2 *, const float2 *, cudaStream_t) __attribute__((weak)); \
-    extern "C" cudaError_t sp_bl_##tag(int, const Params *, int, size_t, cudaStream_t, unsigned *, int *, int *) __attribute__((weak));
+    extern "C" cudaError_t sp_fl_##tag(int, const Params *, int, cudaStream_t, unsigned *, const float2 *, const float2 *, int *) __attribute__((weak));
 SP_DECL(rt) SP_DECL(cu4) SP_DECL(cs4) SP_DECL(cu8) SP_DECL(cs8) SP_DECL(cu12) SP_DECL(cs12) SP_DECL(cu16)
 SP_DECL(cs16) SP_DECL(cu32) SP_DECL(cs32) SP_DECL(cu64) SP_DECL(cs64) SP_DECL(cf32) SP_DECL(cf64)
 
 typedef cudaError_t (*render_fn)(int, const Params *, int, size_t, cudaStream_t, int *);
 typedef cudaError_t (*prepass_fn)(int, const Params *, float2 *, const float2 *, cudaStream_t);
-typedef cudaError_t (*big_fn)(int, const Params *, int, size_t, cudaStream_t, unsigned *, int *, int *);
+typedef cudaError_t (*fast_fn)(int, const Params *, int, cudaStream_t, unsigned *, const float2 *, const float2 *, int *);
 
 static render_fn render_for(int fmt)
 {
@@ -43,11 +43,11 @@ static prepass_fn prepass_for(int fmt)
         sp_pl_cu16, sp_pl_cs16, sp_pl_cu32, sp_pl_cs32, sp_pl_cu64, sp_pl_cs64, sp_pl_cf32, sp_pl_cf64 };
     return tab[fmt] ? tab[fmt] : sp_pl_rt;
 }
-static big_fn big_for(int fmt)
+static fast_fn fast_for(int fmt)
 {
-    static const big_fn tab[SP_FORMAT_COUNT] = { sp_bl_cu4, sp_bl_cs4, sp_bl_cu8, sp_bl_cs8, sp_bl_cu12, sp_bl_cs12,
-        sp_bl_cu16, sp_bl_cs16, sp_bl_cu32, sp_bl_cs32, sp_bl_cu64, sp_bl_cs64, sp_bl_cf32, sp_bl_cf64 };
-    return tab[fmt] ? tab[fmt] : sp_bl_rt;
+    static const fast_fn tab[SP_FORMAT_COUNT] = { sp_fl_cu4, sp_fl_cs4, sp_fl_cu8, sp_fl_cs8, sp_fl_cu12, sp_fl_cs12,
+        sp_fl_cu16, sp_fl_cs16, sp_fl_cu32, sp_fl_cs32, sp_fl_cu64, sp_fl_cs64, sp_fl_cf32, sp_fl_cf64 };
+    return tab[fmt] ? tab[fmt] : sp_fl_rt;
 }
 static bool specialised(int fmt)
 {
@@ -267,6 +267,20 @@ static int get_pass_tables(sp_engine *e, int log2k, const float2 **twA, const fl
     return SP_OK;
 }
 
+// fast-path tables: tw6A [256][6] = W_4096^{t*k}, tw6B [16][6] = W_256^{b*k}, k = 1, 2, 3, 4, 8, 12
+static int get_fast_tables(sp_engine *e, const float2 **tw6A, const float2 **tw6B)
+{
+    static const int ks[6] = { 1, 2, 3, 4, 8, 12 };
+    auto ia = e->twA.find(-4096), ib = e->twB.find(-256);
+    if (ia != e->twA.end() && ib != e->twB.end()) { *tw6A = ia->second; *tw6B = ib->second; return SP_OK; }
+    std::vector<float2> ha((size_t)256 * 6), hb((size_t)16 * 6);
+    for (int t = 0; t < 256; t++) for (int i = 0; i < 6; i++) ha[(size_t)t * 6 + i] = twid((long long)t * ks[i], 4096);
+    for (int b = 0; b < 16; b++) for (int i = 0; i < 6; i++) hb[(size_t)b * 6 + i] = twid((long long)b * ks[i], 256);
+    int rc = upload_table(e, e->twA, -4096, ha, tw6A);
+    if (rc) return rc;
+    return upload_table(e, e->twB, -256, hb, tw6B);
+}
+
 struct Plan {
     int log2k = 0;       // kernel FFT size (log2)
     int sub_r = 1;       // pre-pass radix (n = sub_r * 4096 when > 1)
@@ -303,9 +317,9 @@ extern "C" const char *sp_kernel_plan(sp_engine *e, int format, int n, int chann
     snprintf(buf, sizeof buf, "%s%srender_kernel<N=%d,%s> tile=%d frames smem_x=%d B%s", pl.sub_r > 1 ? "prepass_kernel<R=" : "",
              pl.sub_r > 1 ? (std::to_string(pl.sub_r) + "> + ").c_str() : "", 1 << pl.log2k,
              specialised(format) ? k_names[format] : "runtime-format", pl.tile, pl.smem_x * 8, channel_mode ? " +splitreal" : "");
-    if (pl.log2k == 12 && !channel_mode && !getenv("SP_NO_BIG")) {
+    if (pl.log2k == 12 && !channel_mode && !getenv("SP_NO_FAST")) {
         const size_t l = strlen(buf);
-        snprintf(buf + l, sizeof buf - l, " | spectrogram fast path: render_big_kernel<slots=2,frames=8> (TMA-staged input)");
+        snprintf(buf + l, sizeof buf - l, " | spectrogram fast path: render_fast_kernel<slots=2,frames=8> (TMA-staged input, packed fp32)");
     }
     e->plan = buf;
     return e->plan.c_str();
@@ -500,36 +514,47 @@ static int prepare(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, boo
     return SP_OK;
 }
 
-// N = 4096 fast path (render_big_kernel): spectrogram layout, cmap_len <= 256, width % 4 == 0, image wanted.
-static bool big_eligible(const Params &p)
+// N = 4096 fast path (render_fast_kernel): spectrogram layout, cmap_len <= 256, width % 8 == 0, image wanted.
+static bool fast_eligible(const Params &p)
 {
-    static const bool off = getenv("SP_NO_BIG") != nullptr;
-    return !off && p.image && !p.waterfall && !p.channel_mode && !p.db_out && p.cmap_len <= 256 && (p.nframes % 4 == 0) &&
-           (((uintptr_t)p.image) & 15) == 0;
+    static const bool off = getenv("SP_NO_FAST") != nullptr;
+    return !off && p.image && !p.waterfall && !p.channel_mode && !p.db_out && p.cmap_len <= 256 && (p.nframes % 8 == 0) &&
+           (p.chunk_first % 8 == 0) && (((uintptr_t)p.image) & 31) == 0;
 }
-static int big_variant()
+// Frames [0, *nfast) of the chunk described by q go through the fast kernel: whole tiles of 8 frames that
+// lie entirely inside the buffer (the kernel carries no per-frame predicates); the caller renders the rest.
+static int launch_fast_kernel(sp_engine *e, fast_fn fn, Params &q, long long *nfast)
 {
-    static const int v = getenv("SP_BIG_VARIANT") ? atoi(getenv("SP_BIG_VARIANT")) : 0;
-    return v;
-}
-static int launch_big_kernel(sp_engine *e, big_fn fn, Params &q)
-{
-    const int variant = big_variant();
-    const int slots = (variant == 1 || variant == 2) ? 3 : 2, f = (variant == 1 || variant == 3) ? 4 : 8;
-    int raw_bytes = 0, occ = 0;
-    CU(fn(variant, &q, 0, 0, e->stream, nullptr, nullptr, &raw_bytes));      // query RAW_BYTES
-    const size_t smem = sp::big_smem_bytes(raw_bytes, q.cmap_len, slots, f);
-    CU(fn(variant, &q, 0, smem, e->stream, nullptr, &occ, nullptr));
-    if (occ < 1) return fail(e, SP_E_CUDA, "render_big_kernel does not fit an SM (smem %zu)", smem);
-    int rc = ensure(e, e->tilectr, 256);
+    const bool sub = q.sub_r > 1;
+    long long nf = q.chunk_frames / 8 * 8;
+    if (!sub) {
+        const long long sw = sp::sample_width(q.format);
+        auto inside = [&](long long xr) {
+            const long long xgl = q.frame_first + q.chunk_first + xr;
+            const long long p0 = (long long)(0.5 + q.stride * (double)xgl) - q.sample_base;       // lib/worker.js:72
+            return p0 >= 0 && (unsigned long long)(p0 + 4096) * (unsigned long long)sw <= q.valid_bytes;
+        };
+        while (nf > 0 && !inside(nf - 1)) nf -= 8;
+        if (nf > 0 && !inside(0)) nf = 0;
+    }
+    *nfast = nf;
+    if (nf == 0) return SP_OK;
+    const float2 *tw6A = nullptr, *tw6B = nullptr;
+    int rc = get_fast_tables(e, &tw6A, &tw6B), occ = 0;
     if (rc) return rc;
+    CU(fn(sub ? 1 : 0, &q, 0, e->stream, nullptr, tw6A, tw6B, &occ));
+    if (occ < 1) return fail(e, SP_E_CUDA, "render_fast_kernel does not fit an SM");
+    if ((rc = ensure(e, e->tilectr, 256))) return rc;
     CU(cudaMemsetAsync(e->tilectr.p, 0, 4, e->stream));
-    q.ntiles = ((q.chunk_frames + f - 1) / f) * (q.sub_r > 1 ? q.sub_r : 1);
-    const long long want = (q.ntiles + slots - 1) / slots;
+    Params r = q;
+    r.chunk_frames = nf;
+    r.ntiles = (nf / 8) * (sub ? q.sub_r : 1);
+    const long long want = (r.ntiles + 1) / 2;
     const int grid = (int)(want < e->sm_count ? want : e->sm_count);
     prof_begin(e);
-    CU(fn(variant, &q, grid, smem, e->stream, (unsigned *)e->tilectr.p, nullptr, nullptr));
+    CU(fn(sub ? 1 : 0, &r, grid, e->stream, (unsigned *)e->tilectr.p, tw6A, tw6B, nullptr));
     prof_end(e);
+    e->launches++;
     return SP_OK;
 }
 
@@ -549,22 +574,28 @@ static int enqueue_frames(sp_engine *e, Job &j, Params &p)
     const int fmt = p.format;
     const size_t smem = sp::main_smem_bytes(j.plan.smem_x, p.cmap_len, j.plan.log2k > 8 ? 15 * ((1 << j.plan.log2k) / 256) : 0);
     int occ = 0;
-    if (j.plan.sub_r == 1 && j.plan.log2k == 12 && big_eligible(p) && big_for(fmt)) {
-        int rc = launch_big_kernel(e, big_for(fmt), p);
-        if (rc) return rc;
-        e->launches++;
-    } else if (j.plan.sub_r == 1) {
-        render_fn fn = render_for(fmt);
-        if (!fn) return fail(e, SP_E_CUDA, "no render kernel linked for format %d", fmt);
-        CU(fn(j.plan.log2k, &p, 0, smem, e->stream, &occ));
-        if (occ < 1) return fail(e, SP_E_CUDA, "render kernel does not fit an SM (smem %zu)", smem);
-        p.ntiles = (p.chunk_frames + j.plan.tile - 1) / j.plan.tile;
-        const long long cap = (long long)e->sm_count * occ;
-        const int grid = (int)(p.ntiles < cap ? p.ntiles : cap);
-        prof_begin(e);
-        CU(fn(j.plan.log2k, &p, grid, smem, e->stream, nullptr));
-        prof_end(e);
-        e->launches++;
+    if (j.plan.sub_r == 1) {
+        Params q = p;
+        if (j.plan.log2k == 12 && fast_eligible(p) && fast_for(fmt)) {
+            long long nfast = 0;
+            int rc = launch_fast_kernel(e, fast_for(fmt), q, &nfast);
+            if (rc) return rc;
+            q.chunk_first += nfast;
+            q.chunk_frames -= nfast;
+        }
+        if (q.chunk_frames > 0) {
+            render_fn fn = render_for(fmt);
+            if (!fn) return fail(e, SP_E_CUDA, "no render kernel linked for format %d", fmt);
+            CU(fn(j.plan.log2k, &q, 0, smem, e->stream, &occ));
+            if (occ < 1) return fail(e, SP_E_CUDA, "render kernel does not fit an SM (smem %zu)", smem);
+            q.ntiles = (q.chunk_frames + j.plan.tile - 1) / j.plan.tile;
+            const long long cap = (long long)e->sm_count * occ;
+            const int grid = (int)(q.ntiles < cap ? q.ntiles : cap);
+            prof_begin(e);
+            CU(fn(j.plan.log2k, &q, grid, smem, e->stream, nullptr));
+            prof_end(e);
+            e->launches++;
+        }
     } else {
         // four-step path for n > 4096: radix-R pre-pass into an L2-sized scratch, then the
         // 4096-point kernel in sub-frame mode, chunk by chunk
@@ -594,18 +625,24 @@ static int enqueue_frames(sp_engine *e, Job &j, Params &p)
             q.chunk_frames = (nf - c0 < ch) ? nf - c0 : ch;
             CU(pf(R, &q, (float2 *)e->scratch.p, tw_full, e->stream));
             q.sub_in = (const float2 *)e->scratch.p;
-            big_fn bf = sp_bl_cf32 ? sp_bl_cf32 : sp_bl_rt;
-            if (big_eligible(q) && bf) {
-                if ((rc = launch_big_kernel(e, bf, q))) return rc;
-            } else {
+            fast_fn ff = sp_fl_cf32 ? sp_fl_cf32 : sp_fl_rt;
+            e->launches++;
+            if (fast_eligible(q) && ff) {
+                long long nfast = 0;
+                if ((rc = launch_fast_kernel(e, ff, q, &nfast))) return rc;
+                q.sub_in += (size_t)nfast * (size_t)R * 4096;
+                q.chunk_first += nfast;
+                q.chunk_frames -= nfast;
+            }
+            if (q.chunk_frames > 0) {
                 q.ntiles = ((q.chunk_frames + 7) / 8) * R;
                 const long long cap = (long long)e->sm_count * occ;
                 const int grid = (int)(q.ntiles < cap ? q.ntiles : cap);
                 prof_begin(e);
                 CU(fn(12, &q, grid, smem, e->stream, nullptr));
                 prof_end(e);
+                e->launches++;
             }
-            e->launches += 2;
         }
     }
     return SP_OK;

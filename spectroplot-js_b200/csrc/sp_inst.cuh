@@ -4,7 +4,7 @@
 // specialised formats next to the runtime-switch variant (tag "rt").
 #pragma once
 #include "sp_kernels.cuh"
-#include "sp_kernel_big.cuh"
+#include "sp_kernel_fast.cuh"
 
 namespace sp {
 
@@ -61,38 +61,27 @@ static cudaError_t launch_prepass(int r, const Params &p, float2 *out, const flo
     return cudaGetLastError();
 }
 
-// N = 4096 latency-hiding variant: one CTA of SLOTS x 256 threads per SM, F frames per tile.
-// variant: 0 = 2 slots / 8 frames (default), 1 = 3 slots / 4 frames, 2 = 3 slots / 8 frames, 3 = 2 slots / 4 frames
-template <int FMT, int SLOTS, int F>
-static cudaError_t launch_big_v(const Params &p, int grid, size_t smem, cudaStream_t st, unsigned *tile_counter, int *occ_out)
+// N = 4096 fast path: one CTA of 2 x 256 threads per SM, 8 frames per tile (sp_kernel_fast.cuh).
+template <int FMT, bool SUB>
+static cudaError_t launch_fast_v(const Params &p, int grid, cudaStream_t st, unsigned *tile_counter, const float2 *tw6A,
+                                 const float2 *tw6B, int *occ_out)
 {
-    auto kfn = render_big_kernel<FMT, SLOTS, F>;
+    using B = FastCfg<FMT, SUB>;
+    auto kfn = render_fast_kernel<FMT, SUB>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
     if (occ_out) {
         int nb = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, 256 * SLOTS, smem);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, B::THREADS, B::SMEM_BYTES);
         *occ_out = nb;
         return e;
     }
-    kfn<<<grid, 256 * SLOTS, smem, st>>>(p, tile_counter);
+    kfn<<<grid, B::THREADS, B::SMEM_BYTES, st>>>(p, tw6A, tw6B, tile_counter);
     return cudaGetLastError();
-}
-template <int FMT>
-static cudaError_t launch_big(int variant, const Params &p, int grid, size_t smem, cudaStream_t st, unsigned *tile_counter, int *occ_out)
-{
-    switch (variant) {
-#ifdef SP_BIG_VARIANTS
-    case 1: return launch_big_v<FMT, 3, 4>(p, grid, smem, st, tile_counter, occ_out);
-    case 2: return launch_big_v<FMT, 3, 8>(p, grid, smem, st, tile_counter, occ_out);
-    case 3: return launch_big_v<FMT, 2, 4>(p, grid, smem, st, tile_counter, occ_out);
-#endif
-    default: return launch_big_v<FMT, 2, 8>(p, grid, smem, st, tile_counter, occ_out);
-    }
 }
 
 } // namespace sp
@@ -106,11 +95,14 @@ extern "C" cudaError_t SP_CAT(sp_rl_, SP_INST_TAG)(int log2n, const sp::Params *
 {
     return sp::launch_render<SP_INST_FMT>(log2n, *p, grid, smem, st, occ_out);
 }
-extern "C" cudaError_t SP_CAT(sp_bl_, SP_INST_TAG)(int variant, const sp::Params *p, int grid, size_t smem, cudaStream_t st,
-                                                    unsigned *tile_counter, int *occ_out, int *raw_bytes)
+extern "C" cudaError_t SP_CAT(sp_fl_, SP_INST_TAG)(int sub, const sp::Params *p, int grid, cudaStream_t st, unsigned *tile_counter,
+                                                    const float2 *tw6A, const float2 *tw6B, int *occ_out)
 {
-    if (raw_bytes) { *raw_bytes = sp::BigCfg<SP_INST_FMT, 2, 8>::RAW_BYTES; return cudaSuccess; }   // query only
-    return sp::launch_big<SP_INST_FMT>(variant, *p, grid, smem, st, tile_counter, occ_out);
+    // sub-frame input (four-step path) is always complex fp32: only those two instances carry the SUB variant
+    if constexpr (SP_INST_FMT == sp::CF32 || SP_INST_FMT == sp::FMT_RUNTIME) {
+        if (sub) return sp::launch_fast_v<SP_INST_FMT, true>(*p, grid, st, tile_counter, tw6A, tw6B, occ_out);
+    } else if (sub) return cudaErrorInvalidValue;
+    return sp::launch_fast_v<SP_INST_FMT, false>(*p, grid, st, tile_counter, tw6A, tw6B, occ_out);
 }
 extern "C" cudaError_t SP_CAT(sp_pl_, SP_INST_TAG)(int r, const sp::Params *p, float2 *out, const float2 *tw_full,
                                                     cudaStream_t st)

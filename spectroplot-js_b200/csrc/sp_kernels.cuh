@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
     const float gc5 = p.gc + 0.5f;
     const float l2c_k = -10.0f * p.c1, l2c_k0 = fmaf(-10.0f, p.c0, 2.5f);       // raw cB index = l2c_k * log2|X|^2 + l2c_k0
     const float l2c_g = p.gn * p.c1, l2c_g0 = fmaf(p.gn, p.c0, gc5);             // colour index  = l2c_g * log2|X|^2 + l2c_g0
+    const cf l2c_kg = cpk(l2c_k, l2c_g), l2c_kg0 = cpk(l2c_k0, l2c_g0);
 
     const bool sub = p.sub_r > 1;
     const int nfull = p.n_full;
@@ -197,12 +198,13 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
             const bool active = xr0 + f < p.chunk_frames;
             const long long xr = active ? xr0 + f : p.chunk_frames - 1;   // inactive slots redo the last frame
             const long long xl = p.chunk_first + xr;                      // local frame == image column
-            float2 v[P];
+            cf v[P];
+            bool ragged = false;                                          // frame reads past the end of the buffer
             // ---------------- load + decode + window (lib/worker.js:70-75) ----------------
             if (sub) {
                 const float2 *src = p.sub_in + ((size_t)xr * sub_r + k0sub) * N;
 #pragma unroll
-                for (int a = 0; a < P; a++) v[a] = src[T * a + t];
+                for (int a = 0; a < P; a++) v[a] = cld(src + T * a + t);
             } else {
                 const long long xgl = p.frame_first + xl;
                 // ~~(0.5 + stride * x): separate multiply and add like JavaScript (no FMA)
@@ -211,19 +213,20 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
                     (unsigned long long)(p0 + N) * (unsigned)sample_width(FMT == FMT_RUNTIME ? p.format : FMT) <= p.valid_bytes;
                 if (inside) {
 #pragma unroll
-                    for (int a = 0; a < P; a++) v[a] = decode_raw<FMT>(p.buf, p0 + T * a + t, p.format);
+                    for (int a = 0; a < P; a++) v[a] = cpk(decode_raw<FMT>(p.buf, p0 + T * a + t, p.format));
                 } else {                                       // slow path: frames touching a ragged buffer end
+                    ragged = true;
                     const float inv = 1.0f / raw_scale<FMT>();
 #pragma unroll
                     for (int a = 0; a < P; a++) {
-                        v[a] = decode_checked(p.buf, p0 + T * a + t, p.format, p.valid_bytes);
-                        v[a].x *= inv; v[a].y *= inv;
+                        const float2 d = decode_checked(p.buf, p0 + T * a + t, p.format, p.valid_bytes);
+                        v[a] = cpk(d.x * inv, d.y * inv);
                     }
                 }
                 // raw sample at p0 + n/2 (lib/worker.js:131-133); the power-of-two scale is exact
-                if (t == 0 && active) p.fmid[xl] = make_float2(v[P / 2].x * raw_scale<FMT>(), v[P / 2].y * raw_scale<FMT>());
+                if (t == 0 && active) p.fmid[xl] = make_float2(cre(v[P / 2]) * raw_scale<FMT>(), cim(v[P / 2]) * raw_scale<FMT>());
 #pragma unroll
-                for (int a = 0; a < P; a++) { v[a].x *= win[a]; v[a].y *= win[a]; }
+                for (int a = 0; a < P; a++) v[a] = cscale(v[a], win[a]);
             }
 
             // ---------------- FFT pass A: radix P over the slowest input digit ----------------
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
 #pragma unroll
                 for (int k = 1; k < 16; k++) v[k] = cmul(v[k], __ldg(p.twA + (k - 1) * T + t));   // W_N^{t*k}
 #pragma unroll
-                for (int k = 0; k < 16; k++) bufA[k * C::PITCH_A + t] = v[k];
+                for (int k = 0; k < 16; k++) cst(&bufA[k * C::PITCH_A + t], v[k]);
                 __syncthreads();
             }
             if constexpr (C::PASSES == 3) {
@@ -240,12 +243,12 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
                 constexpr int R2 = C::RL;
                 const int k0 = t / R2, b1 = t % R2;
 #pragma unroll
-                for (int a = 0; a < 16; a++) v[a] = bufA[k0 * C::PITCH_A + R2 * a + b1];
+                for (int a = 0; a < 16; a++) v[a] = cld(&bufA[k0 * C::PITCH_A + R2 * a + b1]);
                 dft<16>(v);
 #pragma unroll
                 for (int k = 1; k < 16; k++) v[k] = cmul(v[k], s_twB[(k - 1) * R2 + b1]);         // W_{N/16}^{b1*k}
 #pragma unroll
-                for (int k = 0; k < 16; k++) bufB[k0 * C::PITCH_B + k * C::P1 + b1] = v[k];
+                for (int k = 0; k < 16; k++) cst(&bufB[k0 * C::PITCH_B + k * C::P1 + b1], v[k]);
                 __syncthreads();
             }
             // ---------------- last pass: NB radix-RL butterflies; v[j*RL + k] is bin kbase[j] + kstep*k ------
@@ -253,9 +256,9 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
 #pragma unroll
                 for (int j = 0; j < C::NB; j++) {
                     const int k0 = t + T * j;
-                    float2 u[C::RL];
+                    cf u[C::RL];
 #pragma unroll
-                    for (int b = 0; b < C::RL; b++) u[b] = bufA[k0 * C::PITCH_A + b];
+                    for (int b = 0; b < C::RL; b++) u[b] = cld(&bufA[k0 * C::PITCH_A + b]);
                     dft<C::RL>(u);
 #pragma unroll
                     for (int b = 0; b < C::RL; b++) v[j * C::RL + b] = u[b];
@@ -264,9 +267,9 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
 #pragma unroll
                 for (int j = 0; j < C::NB; j++) {
                     const int q = t + T * j, k1 = q % 16, k0 = q / 16;
-                    float2 u[C::RL];
+                    cf u[C::RL];
 #pragma unroll
-                    for (int b = 0; b < C::RL; b++) u[b] = bufB[k0 * C::PITCH_B + k1 * C::P1 + b];
+                    for (int b = 0; b < C::RL; b++) u[b] = cld(&bufB[k0 * C::PITCH_B + k1 * C::P1 + b]);
                     dft<C::RL>(u);
 #pragma unroll
                     for (int b = 0; b < C::RL; b++) v[j * C::RL + b] = u[b];
@@ -281,21 +284,21 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
 #pragma unroll
                 for (int j = 0; j < C::NB; j++)
 #pragma unroll
-                    for (int k = 0; k < C::RL; k++) X[kbase[j] + kstep * k] = v[j * C::RL + k];
+                    for (int k = 0; k < C::RL; k++) cst(&X[kbase[j] + kstep * k], v[j * C::RL + k]);
                 __syncthreads();
 #pragma unroll
                 for (int j = 0; j < C::NB; j++)
 #pragma unroll
                     for (int k = 0; k < C::RL; k++) {
                         const int bin = kbase[j] + kstep * k;
-                        const float2 a = v[j * C::RL + k];
+                        const float2 a = cun(v[j * C::RL + k]);
                         const float2 b = X[(N - bin) & (N - 1)];
                         float2 r;
                         if (bin == 0) r = make_float2(a.x, 0.f);
                         else if (bin == N / 2) r = make_float2(0.f, 0.f);
                         else if (bin < N / 2) r = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
                         else r = make_float2(0.5f * (b.y + a.y), 0.5f * (-b.x + a.x));
-                        v[j * C::RL + k] = r;
+                        v[j * C::RL + k] = cpk(r);
                     }
                 __syncthreads();                               // X aliases the exchange buffers
             }
@@ -306,7 +309,8 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
             float vabs[P / 2 > 0 ? P / 2 : 1];
 #pragma unroll
             for (int i = 0; i < P; i++) {
-                const float abs2 = fmaf(v[i].x, v[i].x, v[i].y * v[i].y);
+                const float2 vi = cun(v[i]);
+                const float abs2 = fmaf(vi.x, vi.x, vi.y * vi.y);
                 if (i & 1) {                                 // 3-input min / max (NaN never wins, like `<` in JS)
                     const float prev = vabs[i >> 1];
                     amin = fmin3(amin, prev, abs2);
@@ -314,11 +318,12 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
                 } else vabs[i >> 1] = abs2;
                 const float l2 = fast_log2(abs2);                              // dBfs - gain = c1*l2 + c0 (lib/worker.js:93)
                 // saturating float->uint conversions do the clamping: negative / NaN -> 0, +inf -> max
-                const float kf = fmaf(l2, l2c_k, l2c_k0);
+                const float2 kg = cun(cfma2(cpk(l2, l2), l2c_kg, l2c_kg0));     // one FFMA2: (raw cB index, colour index)
+                const float kf = kg.x;
                 unsigned cr = min(__float2uint_rz(kf), (unsigned)CB_RAW_CAP);                             // :105-106
-                if constexpr (FMT == CF32 || FMT == CF64 || FMT == FMT_RUNTIME)
-                    if (!(fabsf(kf) <= 3.0e9f)) cr = 1;     // NaN / -inf (only float input can do this): ~~v == 0 -> bin 0
-                const unsigned g = min(__float2uint_rz(fmaf(l2, l2c_g, l2c_g0)), cmax_u);                 // :111-112
+                if ((FMT == CF32 || FMT == CF64 || FMT == FMT_RUNTIME) || ragged)
+                    if (!(fabsf(kf) <= 3.0e9f)) cr = 1;     // NaN / -inf (float input, or `undefined` past a ragged end): ~~v == 0 -> bin 0
+                const unsigned g = min(__float2uint_rz(kg.y), cmax_u);                                    // :111-112
                 if (active) {
                     atomicAdd(&s_cb[cr], 1u);
                     atomicAdd(&s_col[g].y, 1u);                             // :113
@@ -337,9 +342,10 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
 #pragma unroll 1
                     for (int k = 0; k < C::RL; k++) {
                         const int i = j * C::RL + k;
-                        float2 vi = v[0];
+                        cf vsel = v[0];
 #pragma unroll
-                        for (int q = 0; q < P; q++) if (q == i) vi = v[q];   // register select, no local memory
+                        for (int q = 0; q < P; q++) if (q == i) vsel = v[q];   // register select, no local memory
+                        const float2 vi = cun(vsel);
                         const int kb = kbase_of<C>(t, j);
                         const int bin = sub ? k0sub + sub_r * (kb + kstep * k) : kb + kstep * k;
                         const float abs2 = fmaf(vi.x, vi.x, vi.y * vi.y);
@@ -453,27 +459,27 @@ __global__ void __launch_bounds__(256) prepass_kernel(const Params p, float2 *__
     const long long p0 = (long long)__dadd_rn(0.5, __dmul_rn(p.stride, (double)xgl)) - p.sample_base;
     const bool inside = p0 >= 0 &&
         (unsigned long long)(p0 + (long long)R * NS) * (unsigned)sample_width(FMT == FMT_RUNTIME ? p.format : FMT) <= p.valid_bytes;
-    float2 v[R];
+    cf v[R];
     if (inside) {
 #pragma unroll
-        for (int a = 0; a < R; a++) v[a] = decode_raw<FMT>(p.buf, p0 + NS * a + b, p.format);
+        for (int a = 0; a < R; a++) v[a] = cpk(decode_raw<FMT>(p.buf, p0 + NS * a + b, p.format));
     } else {
         const float inv = 1.0f / raw_scale<FMT>();
 #pragma unroll
         for (int a = 0; a < R; a++) {
-            v[a] = decode_checked(p.buf, p0 + NS * a + b, p.format, p.valid_bytes);
-            v[a].x *= inv; v[a].y *= inv;
+            const float2 d = decode_checked(p.buf, p0 + NS * a + b, p.format, p.valid_bytes);
+            v[a] = cpk(d.x * inv, d.y * inv);
         }
     }
-    if (b == 0) p.fmid[xl] = make_float2(v[R / 2].x * raw_scale<FMT>(), v[R / 2].y * raw_scale<FMT>());   // sample p0 + n/2
+    if (b == 0) p.fmid[xl] = make_float2(cre(v[R / 2]) * raw_scale<FMT>(), cim(v[R / 2]) * raw_scale<FMT>());   // sample p0 + n/2
 #pragma unroll
-    for (int a = 0; a < R; a++) { const float w = p.window[NS * a + b]; v[a].x *= w; v[a].y *= w; }
+    for (int a = 0; a < R; a++) v[a] = cscale(v[a], p.window[NS * a + b]);
     dft<R>(v);
 #pragma unroll
     for (int k = 1; k < R; k++) v[k] = cmul(v[k], tw_full[b * k]);
     float2 *dst = out + (size_t)xr * R * NS + b;
 #pragma unroll
-    for (int k = 0; k < R; k++) dst[(size_t)k * NS] = v[k];
+    for (int k = 0; k < R; k++) cst(dst + (size_t)k * NS, v[k]);
 }
 
 } // namespace sp

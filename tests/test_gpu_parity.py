@@ -295,7 +295,7 @@ def test_properties_at_scale(engine):
 # ------------------------------------------------------------------ pipelined host path == single shot
 @pytest.mark.parametrize("case", [("CS16", 1024, 1000, 700, False), ("CU8", 256, 4001, 300, False),
                                   ("CS16", 4096, 800, 4096, False), ("CF32", 512, 1500, 512, True),
-                                  ("CF32", 8192, 100, 5000, False)])
+                                  ("CF32", 8192, 200, 5000, False)])
 def test_pipelined_host_path_is_bit_identical(engine, case, monkeypatch):
     """Long host-buffer messages are streamed in frame-range chunks over three CUDA streams
     (H2D / render / D2H overlap); the chunks are shards of the same message, so nothing may change."""
