@@ -217,13 +217,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(3, args.warmup)):
         rp = step()
     barrier()
     eng.profile_enable(args.steps)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
@@ -232,11 +232,21 @@ def run_ours(args):
         rp = step()
     e1.record(stream)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
+    kern_ms = eng.profile_read(args.steps)
+    # nvidia-smi samples every 100 ms and the timed region is a few ms: keep the SAME step running (untimed)
+    # until the sampler has seen >= 0.7 s of this load, so the clock record describes the kernel under load
+    t_load = time.perf_counter()
+    while time.perf_counter() - t_load < max(0.0, 0.7 - ms_total * 1e-3):
+        for _ in range(20):
+            rp = step()
+        torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + timed region + the same step repeated untimed to 0.7 s (nvidia-smi -lms 100)"
     eng.render_finish(rp)
     launches = rp.kernel_launches * args.steps
-    kern_ms = eng.profile_read(args.steps)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -294,7 +304,7 @@ def run_ours(args):
                            "l2": "inputs (419 MB) and outputs (419 MB) per GPU exceed the 126 MB L2; no flush needed",
                            "kernel_plan": eng.kernel_plan(FMT, N_FFT)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "peak_source": how, "kernel": "render_kernel<12,CS16>",
+                             "traffic": traffic, "peak_source": how, "kernel": "render_fast_kernel<CS16> (N=4096 fast path)",
                              "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms, "steps": e2e_steps},

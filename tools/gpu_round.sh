@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, bench, ncu launch list, ncu full capture of the render kernel.
+# One GPU-box visit: parity tests, bench (both arms), ncu launch list, ncu full capture of the render kernel.
 # usage (under gpurun): bash tools/gpu_round.sh [tag]
 TAG=${1:-r1}
 OUT=gpurun_out
@@ -11,6 +11,6 @@ timeout 600 python bench.py --steps 20 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_$TAG.json 2>> $OUT/bench_$TAG.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/ncu_launch_$TAG.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:render_ -s 3 -c 2 -f -o $OUT/prof_$TAG \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:render_ -s 3 -c 1 -f -o $OUT/prof_$TAG \
     python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/ncu_full_$TAG.log 2>&1
 tail -3 $OUT/pytest_gpu_$TAG.log; cat $OUT/bench_$TAG.json; tail -3 $OUT/bench_$TAG.err; ls -la $OUT
