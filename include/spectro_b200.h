@@ -170,6 +170,14 @@ int sp_render(sp_engine *e, const sp_request *rq, sp_reply *rp);
 int sp_render_enqueue(sp_engine *e, const sp_request *rq, sp_reply *rp);
 int sp_render_finish(sp_engine *e, sp_reply *rp);
 
+/* Several zoom levels of ONE capture in one pass over the capture bytes: the buffer crosses PCIe
+ * once (or is bound, if device-resident) and level i is rendered as the message `rq` with
+ * width = widths[i], i.e. with its OWN stride (sampleCount - n)/(widths[i] - 1) exactly as the
+ * reference does when the user zooms (one processData() per zoom step: lib/spectroplot.js:513-527,
+ * 1103-1104; SURVEY.md A.6 — the frames of zoom 1 are not a subset of zoom z's frames).
+ * replies[i] is the reply of level i; rq->width is ignored.  Stops at the first failing level. */
+int sp_render_zooms(sp_engine *e, const sp_request *rq, int nlevels, const int64_t *widths, sp_reply *replies);
+
 /* Test tap: decode `count` samples starting at sample `first` to interleaved
  * fp32 I/Q (iq[2*count], host memory) with the SAME device function the fused
  * kernel uses.  Replaces SampleView.sampleI/Q, lib/samples.js:313-400.

@@ -94,7 +94,7 @@ struct sp_engine {
     DevBuf tilectr, pin[2], pimg[2];         // pipeline: double-buffered input bytes / image tiles
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_comp[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr }, ev_setup = nullptr;
-    DevBuf in, image, fmin, fmax, fmid, gauges, hist, stats, mm, lut, window, scratch, db, synth_lut;
+    DevBuf in, zin, spec, image, fmin, fmax, fmid, gauges, hist, stats, mm, lut, window, scratch, db, synth_lut;
     // state of an enqueued (not yet finished) render
     std::vector<cudaEvent_t> prof0, prof1;   // per-launch timing ring of the render kernel
     long long prof_count = 0;
@@ -179,7 +179,7 @@ extern "C" void sp_destroy(sp_engine *e)
     for (auto &kv : e->tw) cudaFree(kv.second);
     for (auto &kv : e->twA) cudaFree(kv.second);
     for (auto &kv : e->twB) cudaFree(kv.second);
-    DevBuf *bufs[] = { &e->in, &e->image, &e->fmin, &e->fmax, &e->fmid, &e->gauges, &e->hist, &e->stats, &e->mm,
+    DevBuf *bufs[] = { &e->in, &e->zin, &e->spec, &e->image, &e->fmin, &e->fmax, &e->fmid, &e->gauges, &e->hist, &e->stats, &e->mm,
                        &e->lut, &e->window, &e->scratch, &e->db, &e->synth_lut, &e->tilectr, &e->pin[0], &e->pin[1],
                        &e->pimg[0], &e->pimg[1] };
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
@@ -357,7 +357,6 @@ static int validate(sp_engine *e, const sp_request *rq, bool shard, double *samp
     if (l < 0) return fail(e, SP_E_BAD_N, "Length is not a power of 2");          // lib/fft_nayuki.js:39
     if (rq->n < SP_MIN_N || rq->n > SP_MAX_N) return fail(e, SP_E_BAD_N, "n=%d outside [%d, %d]", rq->n, SP_MIN_N, SP_MAX_N);
     if (rq->cmap_len < 2 || rq->cmap_len > SP_MAX_CMAP) return fail(e, SP_E_BAD_CMAP, "cmap_len=%d outside [2, %d]", rq->cmap_len, SP_MAX_CMAP);
-    if (rq->channel_mode && rq->n > 4096) return fail(e, SP_E_BAD_N, "channel_mode (split-real) is implemented for n <= 4096");
     const uint64_t total_bytes = shard ? rq->total_byte_length : rq->byte_length;
     const int64_t total_width = shard ? rq->total_width : rq->width;
     if (total_bytes % (uint64_t)sp::element_size(rq->format))
@@ -614,6 +613,10 @@ static int enqueue_frames(sp_engine *e, Job &j, Params &p)
         if (ch < 8) ch = 8;
         if (ch > p.nframes) ch = (p.nframes + 7) / 8 * 8;
         if ((rc = ensure(e, e->scratch, (size_t)ch * (size_t)n * 8))) return rc;
+        // split-real pairs bin k with bin n-k, which live in different sub-sequences: tap the whole spectrum of the
+        // chunk and finish it in spectrum_epilogue_kernel
+        const bool tap = p.channel_mode != 0;
+        if (tap && (rc = ensure(e, e->spec, (size_t)ch * (size_t)n * 8))) return rc;
         CU(fn(12, &p, 0, smem, e->stream, &occ));
         if (occ < 1) return fail(e, SP_E_CUDA, "render kernel does not fit an SM (smem %zu)", smem);
         const long long nf = p.nframes;
@@ -627,6 +630,8 @@ static int enqueue_frames(sp_engine *e, Job &j, Params &p)
             q.sub_in = (const float2 *)e->scratch.p;
             fast_fn ff = sp_fl_cf32 ? sp_fl_cf32 : sp_fl_rt;
             e->launches++;
+            Params full = q;                                   // what the epilogue kernel sees
+            if (tap) { q.spec_out = (float2 *)e->spec.p; q.image = nullptr; q.db_out = nullptr; q.channel_mode = 0; }
             if (fast_eligible(q) && ff) {
                 long long nfast = 0;
                 if ((rc = launch_fast_kernel(e, ff, q, &nfast))) return rc;
@@ -641,6 +646,13 @@ static int enqueue_frames(sp_engine *e, Job &j, Params &p)
                 prof_begin(e);
                 CU(fn(12, &q, grid, smem, e->stream, nullptr));
                 prof_end(e);
+                e->launches++;
+            }
+            if (tap) {
+                const long long tiles = full.chunk_frames * (n / 256);
+                const long long cap = (long long)e->sm_count * 8;
+                sp::spectrum_epilogue_kernel<<<(unsigned)(tiles < cap ? tiles : cap), 256, (size_t)(sp::CB_RAW + full.cmap_len) * 4, e->stream>>>(
+                    full, (const float2 *)e->spec.p);
                 e->launches++;
             }
         }
@@ -830,6 +842,26 @@ extern "C" int sp_render(sp_engine *e, const sp_request *rq, sp_reply *rp)
         if (rp->c_hist) CU(cudaMemcpyAsync(rp->c_hist, j.d_c, 8 * (size_t)rq->cmap_len, cudaMemcpyDeviceToHost, e->stream));
     }
     return finish(e, rp);
+}
+
+extern "C" int sp_render_zooms(sp_engine *e, const sp_request *rq, int nlevels, const int64_t *widths, sp_reply *replies)
+{
+    if (!e || !rq || !widths || !replies || nlevels < 1) return fail(e, SP_E_INVAL, "null argument or nlevels < 1");
+    if (!rq->buffer) return fail(e, SP_E_INVAL, "buffer is required");
+    sp_request r = *rq;
+    int rc;
+    if (!(rq->flags & SP_F_BUFFER_ON_DEVICE)) {            // one upload shared by every level
+        CU(cudaSetDevice(e->dev));
+        if ((rc = ensure(e, e->zin, rq->byte_length + 16))) return rc;
+        CU(cudaMemcpyAsync(e->zin.p, rq->buffer, rq->byte_length, cudaMemcpyHostToDevice, e->stream));
+        r.buffer = e->zin.p;
+        r.flags |= SP_F_BUFFER_ON_DEVICE;
+    }
+    for (int i = 0; i < nlevels; i++) {
+        r.width = widths[i];
+        if ((rc = sp_render(e, &r, &replies[i]))) return rc;
+    }
+    return SP_OK;
 }
 
 extern "C" int sp_render_db(sp_engine *e, const sp_request *rq, float *db)

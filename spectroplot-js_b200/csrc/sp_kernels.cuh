@@ -42,6 +42,8 @@ struct Params {
     float2 *fmid;                  // per local frame: raw mid sample (amp gauge)
     unsigned long long *cb_hist, *c_hist;
     float *db_out;                 // optional [nframes][n_full] d0 tap
+    float2 *spec_out;              // optional [chunk frames][n_full] complex spectrum tap: the kernel stops after the FFT
+                                   // (split-real for n_full > 4096 is finished by spectrum_epilogue_kernel)
     // sub-frame mode (n_full > kernel N): the kernel transforms n_full/sub_r point
     // sub-sequences produced by the radix-sub_r pre-pass; sub-frame (x, k0) yields the
     // bins k0 + sub_r*k'.  sub_r == 1 is the ordinary mode.
@@ -276,6 +278,20 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
                 }
             }
 
+            // ---------------- optional spectrum tap: hand the bins to spectrum_epilogue_kernel ----------------
+            if (p.spec_out) {
+                if (active) {
+#pragma unroll
+                    for (int j = 0; j < C::NB; j++)
+#pragma unroll
+                        for (int k = 0; k < C::RL; k++) {
+                            const int kk = kbase[j] + kstep * k;
+                            cst(p.spec_out + (size_t)xr * nfull + (sub ? k0sub + sub_r * kk : kk), v[j * C::RL + k]);
+                        }
+                }
+                continue;
+            }
+
             // ---------------- optional split-real post-process (lib/fft_nayuki.js:103-119) ----------------
             if (p.channel_mode) {
                 // (the engine never combines channel mode with sub-frame mode, see sp_engine.cu)
@@ -407,7 +423,7 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
         // ---------------- per-frame min/max across the warps of a slot ----------------
         if constexpr (T > 32) {
             __syncthreads();
-            if (tid < C::SLOTS * C::FRAMES_PER_SLOT) {
+            if (tid < C::SLOTS * C::FRAMES_PER_SLOT && !p.spec_out) {
                 const int s = tid / C::FRAMES_PER_SLOT, f = tid % C::FRAMES_PER_SLOT;
                 const long long xr = xg * C::TILE + (long long)s * C::FRAMES_PER_SLOT + f;
                 if (xr < p.chunk_frames) {
@@ -480,6 +496,76 @@ __global__ void __launch_bounds__(256) prepass_kernel(const Params p, float2 *__
     float2 *dst = out + (size_t)xr * R * NS + b;
 #pragma unroll
     for (int k = 0; k < R; k++) cst(dst + (size_t)k * NS, v[k]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-bin epilogue over a complex spectrum held in global memory (one thread per bin): optional
+// split-real (lib/fft_nayuki.js:103-119), then dB, histograms, colour, pixel, per-frame min / max
+// exactly as render_kernel does them (lib/worker.js:85-125).  Used where the post-process needs
+// bins of different sub-sequences of the four-step FFT together: channelMode with n > 4096.
+// p.fmin / p.fmax hold order-preserving uints (init_minmax_kernel), as in sub-frame mode.
+// ---------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256) spectrum_epilogue_kernel(const Params p, const float2 *__restrict__ spec)
+{
+    extern __shared__ unsigned s_epi[];
+    unsigned *s_cb = s_epi, *s_cnt = s_epi + CB_RAW;
+    for (int i = threadIdx.x; i < CB_RAW + p.cmap_len; i += 256) s_epi[i] = 0;
+    __syncthreads();
+    const int n = p.n_full, per_frame = n / 256;
+    const unsigned cmax_u = (unsigned)(p.cmap_len - 1);
+    const float gc5 = p.gc + 0.5f;
+    const float l2c_k = -10.0f * p.c1, l2c_k0 = fmaf(-10.0f, p.c0, 2.5f);
+    const float l2c_g = p.gn * p.c1, l2c_g0 = fmaf(p.gn, p.c0, gc5);
+    const long long total = p.chunk_frames * per_frame;
+    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const long long xr = tile / per_frame, xl = p.chunk_first + xr;
+        const int bin = (int)(tile % per_frame) * 256 + threadIdx.x;
+        const float2 *X = spec + (size_t)xr * n;
+        float2 r = X[bin];
+        if (p.channel_mode) {
+            const float2 a = r, b = X[(n - bin) & (n - 1)];
+            if (bin == 0) r = make_float2(a.x, 0.f);
+            else if (bin == n / 2) r = make_float2(0.f, 0.f);
+            else if (bin < n / 2) r = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
+            else r = make_float2(0.5f * (b.y + a.y), 0.5f * (-b.x + a.x));
+        }
+        const float abs2 = fmaf(r.x, r.x, r.y * r.y);
+        const float l2 = fast_log2(abs2);
+        const float d0 = fmaf(l2, p.c1, p.c0);
+        const float kf = fmaf(l2, l2c_k, l2c_k0);
+        unsigned cr = min(__float2uint_rz(kf), (unsigned)CB_RAW_CAP);
+        if (!(fabsf(kf) <= 3.0e9f)) cr = 1;                                      // NaN / -inf -> bin 0
+        const unsigned g = min(__float2uint_rz(fmaf(l2, l2c_g, l2c_g0)), cmax_u);
+        atomicAdd(&s_cb[cr], 1u);
+        atomicAdd(&s_cnt[g], 1u);
+        if (p.db_out) p.db_out[(size_t)xl * n + bin] = d0;
+        if (p.image) {
+            const int y = (n / 2 - bin) & (n - 1);                                // lib/worker.js:90
+            const size_t px = p.waterfall ? (size_t)n * (size_t)(p.nframes - 1 - xl) + (size_t)(n - 1 - y)   // :116
+                                          : (size_t)xl + (size_t)p.nframes * (size_t)y;                      // :117
+            reinterpret_cast<uint32_t *>(p.image)[px] = p.lut[g];
+        }
+        float mn = fminf(0.0f, d0), mx = fmaxf(-200.0f, d0);                      // NaN never wins (lib/worker.js:102-103)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(reinterpret_cast<unsigned *>(p.fmin) + xl, f2ord(mn));
+            atomicMax(reinterpret_cast<unsigned *>(p.fmax) + xl, f2ord(mx));
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < CB_RAW; i += 256) {
+        const unsigned c = s_cb[i];
+        if (c) {
+            const int b = cb_bin_of_raw(i);
+            if (b >= 0) atomicAdd(&p.cb_hist[b], (unsigned long long)c);
+        }
+    }
+    for (int i = threadIdx.x; i < p.cmap_len; i += 256)
+        if (s_cnt[i]) atomicAdd(&p.c_hist[i], (unsigned long long)s_cnt[i]);
 }
 
 } // namespace sp

@@ -30,7 +30,7 @@ ERRORS = {0: "SP_OK", -1: "SP_E_INVAL", -2: "SP_E_BAD_N", -3: "SP_E_BAD_FORMAT",
 # every symbol include/spectro_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = ["sp_abi_version", "sp_format_from_name", "sp_format_name", "sp_sample_width", "sp_element_size",
            "sp_create", "sp_destroy", "sp_last_error", "sp_set_stream", "sp_render", "sp_render_enqueue",
-           "sp_render_finish", "sp_decode", "sp_render_db", "sp_device_alloc", "sp_device_free", "sp_memcpy_h2d",
+           "sp_render_finish", "sp_render_zooms", "sp_decode", "sp_render_db", "sp_device_alloc", "sp_device_free", "sp_memcpy_h2d",
            "sp_memcpy_d2h", "sp_host_alloc_pinned", "sp_host_free_pinned", "sp_device_sync", "sp_synth_fill",
            "sp_synth_lut", "sp_device_count", "sp_sm_count", "sp_kernel_plan", "sp_profile_enable", "sp_profile_read"]
 
@@ -84,6 +84,7 @@ def load():
         getattr(lib, fn).argtypes = [C.c_void_p, C.POINTER(Request), C.POINTER(Reply)]
     lib.sp_render_finish.argtypes = [C.c_void_p, C.POINTER(Reply)]
     lib.sp_render_db.argtypes = [C.c_void_p, C.POINTER(Request), C.c_void_p]
+    lib.sp_render_zooms.argtypes = [C.c_void_p, C.POINTER(Request), C.c_int, C.POINTER(C.c_int64), C.POINTER(Reply)]
     lib.sp_decode.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
     lib.sp_device_alloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
     lib.sp_device_free.argtypes = [C.c_void_p, C.c_void_p]
@@ -280,6 +281,30 @@ class Engine:
         return dict(image=img, gauge_mins=gmin, gauge_maxs=gmax, gauge_amps=gamp, cB_hist=cb, c_hist=ch,
                     dBfs_min=rp.dBfs_min, dBfs_max=rp.dBfs_max, device_ms=rp.device_ms,
                     kernel_launches=rp.kernel_launches)
+
+    def render_zooms(self, buf, fmt, n, widths, windowc, block_norm, gain, range_, cmap, channel_mode=False,
+                     waterfall=False):
+        """Several zoom levels of one capture in one pass over its bytes (sp_render_zooms): the capture is
+        uploaded once; level i is the message with width = widths[i] and its own stride.  -> list of reply dicts."""
+        rq, keep = self.make_request(buf, fmt, n, widths[0], windowc, block_norm, gain, range_, cmap, channel_mode, waterfall)
+        n = int(n)
+        nl = len(widths)
+        wl = (C.c_int64 * nl)(*[int(w) for w in widths])
+        rps = (Reply * nl)()
+        outs = []
+        for i, width in enumerate(int(w) for w in widths):
+            img = np.empty(4 * width * n, np.uint8)
+            gmin = np.empty(width, np.uint8); gmax = np.empty(width, np.uint8); gamp = np.empty(width, np.uint8)
+            cb = np.zeros(CB_HIST_SIZE, np.uint64); ch = np.zeros(rq.cmap_len, np.uint64)
+            rps[i] = Reply(_vp(img), _vp(gmin), _vp(gmax), _vp(gamp), _vp(cb), _vp(ch), 0.0, 0.0, 0.0, 0, None)
+            outs.append(dict(image=img, gauge_mins=gmin, gauge_maxs=gmax, gauge_amps=gamp, cB_hist=cb, c_hist=ch))
+        self._check(self.lib.sp_render_zooms(self.h, C.byref(rq), nl, wl, rps))
+        for i, width in enumerate(int(w) for w in widths):
+            o = outs[i]
+            o["image"] = o["image"].reshape((width, n, 4) if waterfall else (n, width, 4))
+            o.update(dBfs_min=rps[i].dBfs_min, dBfs_max=rps[i].dBfs_max, device_ms=rps[i].device_ms,
+                     kernel_launches=rps[i].kernel_launches)
+        return outs
 
     def render_db(self, buf, fmt, n, width, windowc, block_norm, gain, range_, cmap, channel_mode=False) -> np.ndarray:
         rq, keep = self.make_request(buf, fmt, n, width, windowc, block_norm, gain, range_, cmap, channel_mode)

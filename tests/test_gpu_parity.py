@@ -178,10 +178,12 @@ def test_cmap_lengths_and_ranges(engine, cmap_len):
                  label=f"cmap{cmap_len} gain{gain} range{rng}")
 
 
-@pytest.mark.parametrize("n", [64, 1024, 4096])
+@pytest.mark.parametrize("n", [64, 1024, 4096, 8192, 65536])
 def test_channel_mode_and_waterfall(engine, n):
-    width = 16
-    S = n * 16 + 5
+    """split-real (lib/fft_nayuki.js:103-119) and the waterfall layout at every kernel class, including the
+    four-step sizes where bin k and bin n-k come from different sub-sequences."""
+    width = 16 if n <= 8192 else 8
+    S = n * (4 if n > 8192 else 16) + 5
     buf = O.synth("CS16", 0, S, S, 0x5EC77000 + n).tobytes()
     run_both(engine, buf, "CS16", n, width, "hann", channel_mode=True)
     run_both(engine, buf, "CS16", n, width, "hann", waterfall=True)
@@ -314,3 +316,22 @@ def test_pipelined_host_path_is_bit_identical(engine, case, monkeypatch):
     assert one["dBfs_min"] == pipe["dBfs_min"] and one["dBfs_max"] == pipe["dBfs_max"]
     assert pipe["kernel_launches"] > one["kernel_launches"]          # it really was chunked
     pin.free()
+
+
+def test_zoom_levels_in_one_pass(engine):
+    """C3 shape at test size: zoom x1/x2/x4/x8 images of one capture from ONE upload (sp_render_zooms); every level
+    has its own stride and must equal the separately rendered message exactly, and the x1 level must
+    hold parity with the oracle."""
+    fmt, n, base = "CF32", 2048, 24
+    S = n * base + 777
+    buf = O.synth(fmt, 0, S, S, 0x5EC70003).tobytes()
+    w, wt = O.window("blackmanHarris", n)
+    widths = [base * z for z in (1, 2, 4, 8)]
+    outs = engine.render_zooms(buf, fmt, n, widths, w, 1 / wt, 6, 30, CM256)
+    for width, o in zip(widths, outs):
+        one = engine.render(buf, fmt, n, width, w, 1 / wt, 6, 30, CM256)
+        for k in ("image", "cB_hist", "c_hist", "gauge_mins", "gauge_maxs", "gauge_amps"):
+            assert np.array_equal(one[k], o[k]), (width, k)
+        assert one["dBfs_min"] == o["dBfs_min"] and one["dBfs_max"] == o["dBfs_max"]
+    ora = O.render(buf, fmt, n, widths[0], w, 1 / wt, 6, 30, CM256, taps=True)
+    check_parity(outs[0], ora, CM256, n, widths[0], False, None, "zoom x1")
