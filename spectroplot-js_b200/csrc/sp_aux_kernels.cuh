@@ -23,12 +23,21 @@ __device__ __forceinline__ unsigned char u8clamped(double v)
 // gauges (lib/worker.js:128-136) and the message-wide min / max (lib/worker.js:124-125).
 // Many CTAs of 256 frames each; the last CTA to finish converts the folded min/max to doubles.
 // `ordered` says fmin/fmax hold f2ord() encodings (sub-frame mode).  mm = {ordered min, ordered max,
-// done counter}, initialised by finalize_init_kernel.
-__global__ void finalize_init_kernel(unsigned *mm)
+// done counter}, initialised by prep_kernel.
+// One launch that resets everything a render accumulates into: both histograms, the tile counters of the
+// fast kernel (one per launch of the render) and the min / max fold of finalize_kernel.
+constexpr int TILE_COUNTERS = 4096;
+__global__ void __launch_bounds__(256) prep_kernel(unsigned long long *cb, unsigned long long *c, int cmap_len, unsigned *tilectr, unsigned *mm)
 {
-    mm[0] = f2ord(0.0f);        // lib/worker.js:35
-    mm[1] = f2ord(-200.0f);     // lib/worker.js:36
-    mm[2] = 0;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < CB_BINS) cb[i] = 0;
+    if (i < cmap_len) c[i] = 0;
+    if (i < TILE_COUNTERS) tilectr[i] = 0;
+    if (i == 0) {
+        mm[0] = f2ord(0.0f);        // lib/worker.js:35
+        mm[1] = f2ord(-200.0f);     // lib/worker.js:36
+        mm[2] = 0;
+    }
 }
 
 __global__ void __launch_bounds__(256) finalize_kernel(const float *fmin, const float *fmax, const float2 *fmid,

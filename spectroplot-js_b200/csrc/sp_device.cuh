@@ -53,11 +53,20 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf
 // Each matches fround() of the reference's double expression for EVERY code (SURVEY A.1;
 // the three non-power-of-two biases need a correctly rounded IEEE division).
 
-__device__ __forceinline__ float cv_u4(int c) { return __fdiv_rn((float)(2 * c - 15), 15.0f); }       // (c-7.5)*(1/7.5)
+// Correctly rounded x / D for the three non-power-of-two biases without the IEEE-division subroutine:
+// q = x * RN(1/D); r = x - q*D (exact in one FMA); q' = q + r * RN(1/D)  (Markstein).  Verified equal to
+// RN(x / D) for EVERY code of the three formats with exact rational arithmetic (and by test_decode_bit_exact).
+template <int D> __device__ __forceinline__ float div_exact(float x)
+{
+    constexpr float r = 1.0f / (float)D;
+    const float q = __fmul_rn(x, r);
+    return fmaf(fmaf(-q, (float)D, x), r, q);
+}
+__device__ __forceinline__ float cv_u4(int c) { return div_exact<15>((float)(2 * c - 15)); }          // (c-7.5)*(1/7.5)
 __device__ __forceinline__ float cv_s4(int c) { return (float)c * 0.125f; }                           // c*(1/8)
-__device__ __forceinline__ float cv_u8(int c) { return __fdiv_rn((float)(2 * c - 255), 255.0f); }     // (c-127.5)*(1/127.5)
+__device__ __forceinline__ float cv_u8(int c) { return div_exact<255>((float)(2 * c - 255)); }        // (c-127.5)*(1/127.5)
 __device__ __forceinline__ float cv_s8(int c) { return (float)c * 0.0078125f; }                       // c*(1/128)
-__device__ __forceinline__ float cv_u12(int c) { return __fdiv_rn((float)(2 * c - 4095), 4095.0f); }  // (c-2047.5)*(1/2047.5)
+__device__ __forceinline__ float cv_u12(int c) { return div_exact<4095>((float)(2 * c - 4095)); }     // (c-2047.5)*(1/2047.5)
 __device__ __forceinline__ float cv_s12(int c) { return (float)c * 0.00048828125f; }                  // c*(1/2048)
 __device__ __forceinline__ float cv_u16(int c) { return (float)(2 * c - 65535) * 1.52587890625e-05f; }// (c-32767.5)/32768, exact
 __device__ __forceinline__ float cv_s16(int c) { return (float)c * 3.0517578125e-05f; }               // c/32768, exact

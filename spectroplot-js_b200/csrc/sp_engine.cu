@@ -105,6 +105,7 @@ struct sp_engine {
     long long pend_width = 0;
     int pend_cmap_len = 0;
     int launches = 0;
+    int ctr_next = 0;                        // next unused tile counter (reset by prep_kernel)
 };
 
 static thread_local std::string g_create_err;
@@ -543,15 +544,18 @@ static int launch_fast_kernel(sp_engine *e, fast_fn fn, Params &q, long long *nf
     if (rc) return rc;
     CU(fn(sub ? 1 : 0, &q, 0, e->stream, nullptr, tw6A, tw6B, &occ));
     if (occ < 1) return fail(e, SP_E_CUDA, "render_fast_kernel does not fit an SM");
-    if ((rc = ensure(e, e->tilectr, 256))) return rc;
-    CU(cudaMemsetAsync(e->tilectr.p, 0, 4, e->stream));
+    if (e->ctr_next == sp::TILE_COUNTERS) {                // one counter per fast-kernel launch of this render
+        CU(cudaMemsetAsync(e->tilectr.p, 0, 4 * sp::TILE_COUNTERS, e->stream));
+        e->ctr_next = 0;
+    }
+    unsigned *ctr = (unsigned *)e->tilectr.p + e->ctr_next++;
     Params r = q;
     r.chunk_frames = nf;
     r.ntiles = (nf / 8) * (sub ? q.sub_r : 1);
     const long long want = (r.ntiles + 1) / 2;
     const int grid = (int)(want < e->sm_count ? want : e->sm_count);
     prof_begin(e);
-    CU(fn(sub ? 1 : 0, &r, grid, e->stream, (unsigned *)e->tilectr.p, tw6A, tw6B, nullptr));
+    CU(fn(sub ? 1 : 0, &r, grid, e->stream, ctr, tw6A, tw6B, nullptr));
     prof_end(e);
     e->launches++;
     return SP_OK;
@@ -561,9 +565,12 @@ static int launch_fast_kernel(sp_engine *e, fast_fn fn, Params &q, long long *nf
 static int enqueue_begin(sp_engine *e, Job &j)
 {
     e->launches = 0;
+    int rc = ensure(e, e->tilectr, 4 * sp::TILE_COUNTERS);
+    if (rc) return rc;
     CU(cudaEventRecord(e->ev0, e->stream));
-    CU(cudaMemsetAsync(j.d_cb, 0, 8 * SP_CB_HIST_SIZE, e->stream));
-    CU(cudaMemsetAsync(j.d_c, 0, 8 * (size_t)j.p.cmap_len, e->stream));
+    sp::prep_kernel<<<(SP_MAX_CMAP + 255) / 256, 256, 0, e->stream>>>(j.d_cb, j.d_c, j.p.cmap_len, (unsigned *)e->tilectr.p, (unsigned *)e->mm.p);
+    e->ctr_next = 0;
+    e->launches++;
     return SP_OK;
 }
 
@@ -606,9 +613,11 @@ static int enqueue_frames(sp_engine *e, Job &j, Params &p)
         const float2 *tw_full = nullptr;
         int rc = get_twiddles(e, n, &tw_full);
         if (rc) return rc;
-        size_t scratch_mb = 96;
-        if (const char *s = getenv("SP_SCRATCH_MB")) scratch_mb = (size_t)atoi(s) > 0 ? (size_t)atoi(s) : scratch_mb;
-        long long ch = (long long)((scratch_mb << 20) / ((size_t)n * 8));
+        // chunk = one full wave of the sub-frame kernel: 2 slots x sm_count tiles of 8 sub-frames (77.6 MB of
+        // scratch on 148 SMs, L2 resident); SP_SCRATCH_MB overrides
+        long long ch = (long long)8 * 2 * e->sm_count / R;
+        if (const char *s = getenv("SP_SCRATCH_MB"))
+            if (atoi(s) > 0) ch = (long long)(((size_t)atoi(s) << 20) / ((size_t)n * 8));
         ch = ch / 8 * 8;
         if (ch < 8) ch = 8;
         if (ch > p.nframes) ch = (p.nframes + 7) / 8 * 8;
@@ -663,11 +672,10 @@ static int enqueue_frames(sp_engine *e, Job &j, Params &p)
 static int enqueue_end(sp_engine *e, Job &j)
 {
     Params &p = j.p;
-    sp::finalize_init_kernel<<<1, 1, 0, e->stream>>>((unsigned *)e->mm.p);
     sp::finalize_kernel<<<(unsigned)((p.nframes + 255) / 256), 256, 0, e->stream>>>(
         p.fmin, p.fmax, p.fmid, p.nframes, j.range, j.gain, j.plan.sub_r > 1 ? 1 : 0, j.d_gmin, j.d_gmax, j.d_gamp,
         (unsigned *)e->mm.p, j.d_stats);
-    e->launches += 2;
+    e->launches++;
     CU(cudaGetLastError());
     CU(cudaEventRecord(e->ev1, e->stream));
     return SP_OK;

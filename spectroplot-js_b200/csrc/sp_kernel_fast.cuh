@@ -13,8 +13,10 @@
 //   * per pass only SIX twiddles are loaded (w^1, w^2, w^3, w^4, w^8, w^12; three LDS.128) and the
 //     other nine are formed as products in registers — the kernel is bound by the shared-memory /
 //     LSU data pipe, not by the FMA pipe (ncu: profiles/r01_ncu_summary_p1_packed.txt);
-//   * ONE padded exchange buffer per slot is reused in place by both exchanges
-//     (element (k0, a, b) at k0*272 + 17*a + b: every access pattern is bank-conflict free);
+//   * a padded exchange buffer per slot is reused in place by both exchanges (element (k0, a, b) at
+//     k0*272 + 17*a + b: every access pattern is bank-conflict free); where shared memory allows
+//     (<= 4 bytes per sample) two such buffers alternate per frame, so a frame costs two slot
+//     barriers, not three;
 //   * colour indices of 8 consecutive frames are packed in registers and each image row segment
 //     (8 frames x RGBA = one 32-byte sector) is written with ONE 256-bit store (STG.E.ENL2.256) —
 //     the transposed store of lib/worker.js:117;
@@ -33,14 +35,18 @@ namespace sp {
 
 template <int FMT, bool SUB> struct FastCfg {
     static constexpr int N = 4096, T = 256, SLOTS = 2, THREADS = T * SLOTS, F = 8;
-    static constexpr int SWB = sample_width(FMT == FMT_RUNTIME ? CF64 : FMT);
-    static constexpr bool STAGE = !SUB && (FMT != FMT_RUNTIME) && SWB <= 8;      // TMA-staged input
+    // sub-frame mode reads complex fp32 sub-sequences written by the pre-pass, whatever the capture format is
+    static constexpr int SWB = SUB ? 8 : sample_width(FMT == FMT_RUNTIME ? CF64 : FMT);
+    static constexpr bool STAGE = SUB || ((FMT != FMT_RUNTIME) && SWB <= 8);     // TMA-staged input
     static constexpr int RAW_BYTES = STAGE ? N * SWB + 32 : 0;
     static constexpr int PA = 272, P1 = 17;                                      // exchange pitches (float2)
     static constexpr int X_FLOAT2 = 16 * PA;
     static constexpr int WIN_PITCH = 20;                                         // floats per thread row (16 used): conflict-free LDS.128
     static constexpr int TW_PITCH = 6;                                           // float2 per row: w^1 w^2 w^3 w^4 w^8 w^12
-    static constexpr size_t SLOT_BYTES = (size_t)X_FLOAT2 * 8 + RAW_BYTES + 2 * F * 8 * 8 + 64;
+    // two exchange buffers (alternating per frame) remove the write-after-read barrier between consecutive
+    // frames; they fit next to a staged frame of up to 4 bytes per sample
+    static constexpr bool DBX = STAGE && RAW_BYTES <= 4096 * 4 + 32;
+    static constexpr size_t SLOT_BYTES = (size_t)X_FLOAT2 * 8 * (DBX ? 2 : 1) + RAW_BYTES + 2 * F * 8 * 8 + 2 * F * 16 + 64;
     static constexpr size_t SHARED_BYTES = (size_t)T * TW_PITCH * 8 + 16 * TW_PITCH * 8 + (SUB ? 0 : (size_t)T * WIN_PITCH * 4)
                                          + (size_t)CB_RAW * 4 + 256 * 4 + 256 * 4;
     static constexpr size_t SMEM_BYTES = SHARED_BYTES + SLOTS * SLOT_BYTES + 128;
@@ -118,10 +124,11 @@ __global__ void __launch_bounds__(512, 1) render_fast_kernel(const Params p, con
     const int slot = tid / T;
     const int t = tid % T;
     unsigned char *my = slot_base + (size_t)slot * B::SLOT_BYTES;
-    float2 *X = reinterpret_cast<float2 *>(my);                                  // [16][272] in-place exchange
-    unsigned char *raw = my + (size_t)B::X_FLOAT2 * 8;                           // [RAW_BYTES] TMA destination
+    float2 *X0 = reinterpret_cast<float2 *>(my);                                 // [1 or 2][16][272] in-place exchange
+    unsigned char *raw = my + (size_t)B::X_FLOAT2 * 8 * (B::DBX ? 2 : 1);        // [RAW_BYTES] TMA destination
     uint2 *s_mm = reinterpret_cast<uint2 *>(raw + B::RAW_BYTES);                 // [2][F][8] per-warp min/max bit patterns of |X|^2
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(s_mm + 2 * F * 8);
+    ulonglong2 *s_pos = reinterpret_cast<ulonglong2 *>(s_mm + 2 * F * 8);        // [2][F] {source address, bytes | misalignment << 32}
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(s_pos + 2 * F);
     int *s_off = reinterpret_cast<int *>(mbar + 1);                              // [2] byte misalignment of the staged frame (by frame parity)
     unsigned *s_next = reinterpret_cast<unsigned *>(s_off + 2);                  // [2] tile ring
 
@@ -147,12 +154,26 @@ __global__ void __launch_bounds__(512, 1) render_fast_kernel(const Params p, con
     };
     // tile -> first chunk-relative frame
     auto tile_xr0 = [&](long long tile) -> long long { return (SUB ? tile / sub_r : tile) * F; };
-    // t == 0 of a slot: stage frame xr (always inside the buffer) and publish its misalignment
-    auto stage = [&](long long xr, int par) {
-        const long long p0 = frame_p0(xr);
-        const unsigned long long off = (unsigned long long)p0 * B::SWB, a0 = off & ~15ull;
-        s_off[par] = (int)(off - a0);
-        tma_load_1d(raw, p.buf + a0, (unsigned)(((off - a0) + (unsigned long long)N * B::SWB + 15) & ~15ull), mbar);
+    // lanes 0..7 of a slot's first warp, once per tile: where the 8 frames of tile `tl` start (always inside the buffer)
+    auto compute_positions = [&](int rg, long long tl) {
+        const long long xr = tile_xr0(tl) + t;
+        ulonglong2 e;
+        if constexpr (SUB) {
+            e.x = reinterpret_cast<unsigned long long>(p.sub_in + ((size_t)xr * sub_r + (size_t)(tl % sub_r)) * N);
+            e.y = (unsigned long long)(N * 8);
+        } else {
+            const long long p0 = frame_p0(xr);
+            const unsigned long long off = (unsigned long long)p0 * B::SWB, a0 = off & ~15ull;
+            e.x = reinterpret_cast<unsigned long long>(p.buf + a0);
+            e.y = (((off - a0) + (unsigned long long)N * B::SWB + 15) & ~15ull) | ((off - a0) << 32);
+        }
+        s_pos[rg * F + t] = e;
+    };
+    // t == 0 of a slot: start the bulk copy of frame fi of the tile in ring slot rg and publish its misalignment
+    auto stage = [&](int rg, int fi, int par) {
+        const ulonglong2 e = s_pos[rg * F + fi];
+        s_off[par] = (int)(e.y >> 32);
+        tma_load_1d(raw, reinterpret_cast<const void *>(e.x), (unsigned)e.y, mbar);
     };
 
     if (t == 0) {
@@ -162,8 +183,13 @@ __global__ void __launch_bounds__(512, 1) render_fast_kernel(const Params p, con
     }
     __syncthreads();
     long long tile = s_next[0];
-    if constexpr (B::STAGE)
-        if (t == 0 && tile < p.ntiles) stage(tile_xr0(tile), 0);
+    if constexpr (B::STAGE) {
+        if (t < 32 && tile < p.ntiles) {
+            if (t < F) compute_positions(0, tile);
+            __syncwarp();
+            if (t == 0) stage(0, 0, 0);
+        }
+    }
 
     // per-frame min/max of the previous tile of this slot, folded across its 8 warps and converted to dB
     auto publish_minmax = [&](long long pxr0, int pring) {
@@ -200,9 +226,9 @@ __global__ void __launch_bounds__(512, 1) render_fast_kernel(const Params p, con
             cf v[16];
             // ---------------- load + decode + window (lib/worker.js:70-75) ----------------
             if constexpr (SUB) {
-                const float2 *src = p.sub_in + ((size_t)(xr0 + f) * sub_r + k0sub) * N;
+                mbar_wait(mbar, fpar);
 #pragma unroll
-                for (int a = 0; a < 16; a++) v[a] = cpk(__ldg(src + T * a + t));
+                for (int a = 0; a < 16; a++) v[a] = cld(reinterpret_cast<const float2 *>(raw) + T * a + t);
             } else {
                 if constexpr (B::STAGE) {
                     mbar_wait(mbar, fpar);
@@ -232,23 +258,40 @@ __global__ void __launch_bounds__(512, 1) render_fast_kernel(const Params p, con
                 const float4 *tw = reinterpret_cast<const float4 *>(s_twA + t * B::TW_PITCH);      // W_4096^{t*k}
                 twiddle16_from6(v, tw[0], tw[1], tw[2]);
             }
-            slot_barrier(slot);          // X is free (previous frame's pass-C reads) and raw is consumed
-            if (t == 0) {
-                // tile bookkeeping: ask for the tile after this one early, park the answer one frame later
-                if (f == 0) fetched = atomicAdd(tile_counter, 1u);
-                if (f == 1) s_next[ring ^ 1] = fetched;
-                if constexpr (B::STAGE) {   // stage the next frame of this slot while this one is transformed
-                    if (f < F - 1) stage(xr0 + f + 1, fpar);
-                    else if ((long long)fetched < p.ntiles) stage(tile_xr0((long long)fetched), fpar);
+            float2 *X = X0 + (B::DBX ? (int)fpar * B::X_FLOAT2 : 0);
+            // bookkeeping of the slot's first warp, behind the first barrier of the frame (raw is consumed by then):
+            // ask for the tile after this one early, park the answer one frame later, lay out its frame positions
+            // another frame later, and stage the next frame of this slot while this one is transformed
+            auto bookkeeping = [&]() {
+                if (t < 32) {
+                    if (t == 0) {
+                        if (f == 0) fetched = atomicAdd(tile_counter, 1u);
+                        if (f == 1) s_next[ring ^ 1] = fetched;
+                    }
+                    if constexpr (B::STAGE) {
+                        if (f == 2) {
+                            const long long nt = (long long)__shfl_sync(0xffffffffu, fetched, 0);
+                            if (t < F && nt < p.ntiles) compute_positions(ring ^ 1, nt);
+                        }
+                        if (t == 0) {
+                            if (f < F - 1) stage(ring, f + 1, fpar);
+                            else if ((long long)fetched < p.ntiles) stage(ring ^ 1, 0, fpar);
+                        }
+                    }
                 }
+                if (f == 0 && prev_xr0 >= 0) publish_minmax(prev_xr0, ring ^ 1);
+            };
+            if constexpr (!B::DBX) {
+                slot_barrier(slot);      // X is free (previous frame's pass-C reads) and raw is consumed
+                bookkeeping();
             }
-            if (f == 0 && prev_xr0 >= 0) publish_minmax(prev_xr0, ring ^ 1);
             {   // element (k, a1 = t/16, b1 = t%16)
                 float2 *dst = X + B::P1 * k0p + lo4;
 #pragma unroll
                 for (int k = 0; k < 16; k++) cst(dst + k * B::PA, v[k]);
             }
             slot_barrier(slot);
+            if constexpr (B::DBX) bookkeeping();
             // ---------------- pass B: thread (k0, b1), in place ----------------
             {
                 float2 *col = X + k0p * B::PA + lo4;
