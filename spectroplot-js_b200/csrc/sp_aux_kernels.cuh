@@ -27,10 +27,12 @@ __device__ __forceinline__ unsigned char u8clamped(double v)
 // One launch that resets everything a render accumulates into: both histograms, the tile counters of the
 // fast kernel (one per launch of the render) and the min / max fold of finalize_kernel.
 constexpr int TILE_COUNTERS = 4096;
-__global__ void __launch_bounds__(256) prep_kernel(unsigned long long *cb, unsigned long long *c, int cmap_len, unsigned *tilectr, unsigned *mm)
+__global__ void __launch_bounds__(256) prep_kernel(unsigned long long *cb, unsigned long long *c, int cmap_len, unsigned *tilectr, unsigned *mm,
+                                                   unsigned long long *jh)
 {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i < CB_BINS) cb[i] = 0;
+    if (i < JH_SIZE) jh[i] = 0;
     if (i < cmap_len) c[i] = 0;
     if (i < TILE_COUNTERS) tilectr[i] = 0;
     if (i == 0) {
@@ -43,9 +45,27 @@ __global__ void __launch_bounds__(256) prep_kernel(unsigned long long *cb, unsig
 __global__ void __launch_bounds__(256) finalize_kernel(const float *fmin, const float *fmax, const float2 *fmid,
                                                        long long nframes, double range, double gain, int ordered,
                                                        unsigned char *gmin, unsigned char *gmax, unsigned char *gamp,
-                                                       unsigned *mm, double *stats /* [2] min, max */)
+                                                       unsigned *mm, double *stats /* [2] min, max */,
+                                                       const unsigned long long *jh, JhConst jc, int cmap_len,
+                                                       unsigned long long *cb_hist, unsigned long long *c_hist)
 {
     __shared__ float s_mn[8], s_mx[8];
+    // joint histogram of render_r64_kernel -> the reference's two histograms (lib/worker.js:106,113)
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < JH_SIZE; j += gridDim.x * blockDim.x) {
+        const unsigned long long c = jh[j];
+        if (!c) continue;
+        if (j == JH_ZERO) {                          // d0 = -inf pixels were counted in bin 999: they belong to bin 0
+            atomicAdd(&cb_hist[0], c);
+            atomicAdd(&cb_hist[CB_BINS - 1], 0ull - c);
+        } else if (j == JH_BAD) {                    // d0 = +inf / NaN pixels were dropped: they belong to bin 0
+            atomicAdd(&cb_hist[0], c);
+        } else if (j < JH_BINS) {
+            int bin, g;
+            jh_decode(j, jc, cmap_len - 1, bin, g);
+            if (bin >= 0) atomicAdd(&cb_hist[bin], c);
+            atomicAdd(&c_hist[g < 0 ? 0 : g], c);
+        }
+    }
     float mn = 0.0f, mx = -200.0f;
     const long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (x < nframes) {

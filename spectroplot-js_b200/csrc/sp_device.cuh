@@ -348,12 +348,22 @@ template <> __device__ __forceinline__ void dft<8>(cf (&v)[8])
     // n = 4*n1 + n0, k = k0 + 2*k1 :  W8^{nk} = W2^{n1 k0} * W8^{n0 k0} * W4^{n0 k1}
 #pragma unroll
     for (int n0 = 0; n0 < 4; n0++) dft2(v[n0], v[4 + n0]);       // v[n0] : k0 = 0, v[4+n0] : k0 = 1
-    // k0 = 1 row times W8^{n0}
-    v[5] = mul_w8_1(v[5]);
-    v[6] = mul_mj(v[6]);
-    v[7] = mul_w8_3(v[7]);
     dft4(v[0], v[1], v[2], v[3]);   // k0 = 0 : outputs k = 0,2,4,6
-    dft4(v[4], v[5], v[6], v[7]);   // k0 = 1 : outputs k = 1,3,5,7
+    // k0 = 1 : DFT-4 of (x4, W8^1 x5, -j x6, W8^3 x7) with the 1/sqrt2 of the two odd twiddles folded into the
+    // FFMA2 of the last butterfly stage (10 packed instructions instead of 12):
+    //   W8^1 x5 = s*c5, c5 = x5 - j x5;   W8^3 x7 = -s*c7, c7 = x7 + j x7
+    {
+        const cf c5 = cadd(v[5], mul_mj(v[5])), c7 = cadd(v[7], mul_pj(v[7]));
+        const cf d = csub(c5, c7), e = cadd(c5, c7);               // (a1 + a3)/s, (a1 - a3)/s
+        const cf m6 = mul_mj(v[6]);
+        const cf t0 = cadd(v[4], m6), t1 = csub(v[4], m6);
+        const float2 ef = cun(e);
+        const cf es = cpk(ef.y, ef.x);                             // swapped halves: -j*e = (e.im, -e.re)
+        v[4] = cfma2(d, cpk(SP_SQRT1_2, SP_SQRT1_2), t0);          // k1 = 0
+        v[6] = cfma2(d, cpk(-SP_SQRT1_2, -SP_SQRT1_2), t0);        // k1 = 2
+        v[5] = cfma2(es, cpk(SP_SQRT1_2, -SP_SQRT1_2), t1);        // k1 = 1
+        v[7] = cfma2(es, cpk(-SP_SQRT1_2, SP_SQRT1_2), t1);        // k1 = 3
+    }
     cf y[8];
 #pragma unroll
     for (int k1 = 0; k1 < 4; k1++) { y[2 * k1] = v[k1]; y[2 * k1 + 1] = v[4 + k1]; }
@@ -388,6 +398,72 @@ template <> __device__ __forceinline__ void dft<16>(cf (&v)[16])
         for (int k1 = 0; k1 < 4; k1++) y[k0 + 4 * k1] = v[4 * k0 + k1];
 #pragma unroll
     for (int i = 0; i < 16; i++) v[i] = y[i];
+}
+
+// ------------------------------------------------------------------ 64-point DFT in registers
+// cos(2 pi q / 64), q = 0..16 (double -> fp32 once); the other 47 come from the symmetries
+__host__ __device__ constexpr float cos64_q(int q)
+{
+    constexpr float C[17] = { 1.0f, 0.99518472667219693f, 0.98078528040323043f, 0.95694033573220882f, 0.92387953251128674f,
+                              0.88192126434835505f, 0.83146961230254524f, 0.77301045336273699f, 0.70710678118654757f,
+                              0.63439328416364549f, 0.55557023301960229f, 0.47139673682599781f, 0.38268343236508984f,
+                              0.29028467725446233f, 0.19509032201612833f, 0.09801714032956077f, 0.0f };
+    return C[q];
+}
+__host__ __device__ constexpr float cos64(int m)
+{
+    int q = m & 63;
+    if (q > 32) q = 64 - q;
+    return q > 16 ? -cos64_q(32 - q) : cos64_q(q);
+}
+__host__ __device__ constexpr float sin64(int m) { return cos64(m + 48); }     // sin(x) = cos(x - pi/2)
+
+// a * W64^M (forward sign: exp(-2 pi j M / 64)), M a compile-time constant
+template <int M> __device__ __forceinline__ cf mul_w64(cf a)
+{
+    constexpr int m = M & 63;
+    if constexpr (m == 0) return a;
+    else if constexpr (m == 16) return mul_mj(a);
+    else if constexpr (m == 32) return cpk(-cre(a), -cim(a));
+    else if constexpr (m == 48) return mul_pj(a);
+    else return cmul(a, make_float2(cos64(m), -sin64(m)));
+}
+
+template <int K0> __device__ __forceinline__ void dft64_twiddle_row(cf (&v)[64])
+{
+    // element v[8*K0 + n0] holds the k0 = K0 output of column n0: times W64^{n0*K0}
+    v[8 * K0 + 1] = mul_w64<1 * K0>(v[8 * K0 + 1]); v[8 * K0 + 2] = mul_w64<2 * K0>(v[8 * K0 + 2]);
+    v[8 * K0 + 3] = mul_w64<3 * K0>(v[8 * K0 + 3]); v[8 * K0 + 4] = mul_w64<4 * K0>(v[8 * K0 + 4]);
+    v[8 * K0 + 5] = mul_w64<5 * K0>(v[8 * K0 + 5]); v[8 * K0 + 6] = mul_w64<6 * K0>(v[8 * K0 + 6]);
+    v[8 * K0 + 7] = mul_w64<7 * K0>(v[8 * K0 + 7]);
+}
+
+// n = 8*n1 + n0, k = k0 + 8*k1 :  W64^{nk} = W8^{n1 k0} * W64^{n0 k0} * W8^{n0 k1}; natural order in and out
+template <> __device__ __forceinline__ void dft<64>(cf (&v)[64])
+{
+#pragma unroll
+    for (int n0 = 0; n0 < 8; n0++) {                       // DFT-8 over n1 of column n0; result k0 -> v[8*k0 + n0]
+        cf u[8];
+#pragma unroll
+        for (int n1 = 0; n1 < 8; n1++) u[n1] = v[8 * n1 + n0];
+        dft<8>(u);
+#pragma unroll
+        for (int k0 = 0; k0 < 8; k0++) v[8 * k0 + n0] = u[k0];
+    }
+    dft64_twiddle_row<1>(v); dft64_twiddle_row<2>(v); dft64_twiddle_row<3>(v); dft64_twiddle_row<4>(v);
+    dft64_twiddle_row<5>(v); dft64_twiddle_row<6>(v); dft64_twiddle_row<7>(v);
+    cf y[64];
+#pragma unroll
+    for (int k0 = 0; k0 < 8; k0++) {                       // DFT-8 over n0 of row k0; result k1 -> bin k0 + 8*k1
+        cf u[8];
+#pragma unroll
+        for (int n0 = 0; n0 < 8; n0++) u[n0] = v[8 * k0 + n0];
+        dft<8>(u);
+#pragma unroll
+        for (int k1 = 0; k1 < 8; k1++) y[k0 + 8 * k1] = u[k1];
+    }
+#pragma unroll
+    for (int i = 0; i < 64; i++) v[i] = y[i];
 }
 
 } // namespace sp

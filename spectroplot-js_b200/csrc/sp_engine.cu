@@ -6,6 +6,7 @@
 #include "../../include/spectro_b200.h"
 #include "sp_aux_kernels.cuh"
 #include "sp_kernel_fast.cuh"
+#include "sp_kernel_r64.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -23,13 +24,15 @@ using sp::Params;
 #define SP_DECL(tag)                                                                                             \
     extern "C" cudaError_t sp_rl_##tag(int, const Params *, int, size_t, cudaStream_t, int *) __attribute__((weak)); \
     extern "C" cudaError_t sp_pl_##tag(int, const Params *, float2 *, const float2 *, cudaStream_t) __attribute__((weak)); \
-    extern "C" cudaError_t sp_fl_##tag(int, const Params *, int, cudaStream_t, unsigned *, const float2 *, const float2 *, int *) __attribute__((weak));
+    extern "C" cudaError_t sp_fl_##tag(int, const Params *, int, cudaStream_t, unsigned *, const float2 *, const float2 *, int *) __attribute__((weak)); \
+    extern "C" cudaError_t sp_r64_##tag(int, const Params *, int, cudaStream_t, unsigned *, const float2 *, int *) __attribute__((weak));
 SP_DECL(rt) SP_DECL(cu4) SP_DECL(cs4) SP_DECL(cu8) SP_DECL(cs8) SP_DECL(cu12) SP_DECL(cs12) SP_DECL(cu16)
 SP_DECL(cs16) SP_DECL(cu32) SP_DECL(cs32) SP_DECL(cu64) SP_DECL(cs64) SP_DECL(cf32) SP_DECL(cf64)
 
 typedef cudaError_t (*render_fn)(int, const Params *, int, size_t, cudaStream_t, int *);
 typedef cudaError_t (*prepass_fn)(int, const Params *, float2 *, const float2 *, cudaStream_t);
 typedef cudaError_t (*fast_fn)(int, const Params *, int, cudaStream_t, unsigned *, const float2 *, const float2 *, int *);
+typedef cudaError_t (*r64_fn)(int, const Params *, int, cudaStream_t, unsigned *, const float2 *, int *);
 
 static render_fn render_for(int fmt)
 {
@@ -48,6 +51,12 @@ static fast_fn fast_for(int fmt)
     static const fast_fn tab[SP_FORMAT_COUNT] = { sp_fl_cu4, sp_fl_cs4, sp_fl_cu8, sp_fl_cs8, sp_fl_cu12, sp_fl_cs12,
         sp_fl_cu16, sp_fl_cs16, sp_fl_cu32, sp_fl_cs32, sp_fl_cu64, sp_fl_cs64, sp_fl_cf32, sp_fl_cf64 };
     return tab[fmt] ? tab[fmt] : sp_fl_rt;
+}
+static r64_fn r64_for(int fmt)
+{
+    static const r64_fn tab[SP_FORMAT_COUNT] = { sp_r64_cu4, sp_r64_cs4, sp_r64_cu8, sp_r64_cs8, sp_r64_cu12, sp_r64_cs12,
+        sp_r64_cu16, sp_r64_cs16, sp_r64_cu32, sp_r64_cs32, sp_r64_cu64, sp_r64_cs64, sp_r64_cf32, sp_r64_cf64 };
+    return tab[fmt];                                    // specialised formats only (the runtime-switch build has no raw staging)
 }
 static bool specialised(int fmt)
 {
@@ -94,7 +103,7 @@ struct sp_engine {
     DevBuf tilectr, pin[2], pimg[2];         // pipeline: double-buffered input bytes / image tiles
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_comp[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr }, ev_setup = nullptr;
-    DevBuf in, zin, spec, image, fmin, fmax, fmid, gauges, hist, stats, mm, lut, window, scratch, db, synth_lut;
+    DevBuf in, zin, spec, image, fmin, fmax, fmid, gauges, hist, jhist, stats, mm, lut, window, scratch, db, synth_lut;
     // state of an enqueued (not yet finished) render
     std::vector<cudaEvent_t> prof0, prof1;   // per-launch timing ring of the render kernel
     long long prof_count = 0;
@@ -180,7 +189,7 @@ extern "C" void sp_destroy(sp_engine *e)
     for (auto &kv : e->tw) cudaFree(kv.second);
     for (auto &kv : e->twA) cudaFree(kv.second);
     for (auto &kv : e->twB) cudaFree(kv.second);
-    DevBuf *bufs[] = { &e->in, &e->zin, &e->spec, &e->image, &e->fmin, &e->fmax, &e->fmid, &e->gauges, &e->hist, &e->stats, &e->mm,
+    DevBuf *bufs[] = { &e->in, &e->zin, &e->spec, &e->image, &e->fmin, &e->fmax, &e->fmid, &e->gauges, &e->hist, &e->jhist, &e->stats, &e->mm,
                        &e->lut, &e->window, &e->scratch, &e->db, &e->synth_lut, &e->tilectr, &e->pin[0], &e->pin[1],
                        &e->pimg[0], &e->pimg[1] };
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
@@ -282,6 +291,24 @@ static int get_fast_tables(sp_engine *e, const float2 **tw6A, const float2 **tw6
     return upload_table(e, e->twB, -256, hb, tw6B);
 }
 
+// 64 x 64 path table: tw14 [64][14] = W_4096^{t*k}, k = 1..7, 8, 16, .., 56
+static int get_r64_table(sp_engine *e, const float2 **tw14)
+{
+    static const int ks[14] = { 1, 2, 3, 4, 5, 6, 7, 8, 16, 24, 32, 40, 48, 56 };
+    auto it = e->twA.find(-64);
+    if (it != e->twA.end()) { *tw14 = it->second; return SP_OK; }
+    std::vector<float2> h((size_t)64 * 14);
+    for (int t = 0; t < 64; t++) for (int i = 0; i < 14; i++) h[(size_t)t * 14 + i] = twid((long long)t * ks[i], 4096);
+    return upload_table(e, e->twA, -64, h, tw14);
+}
+
+// Which N = 4096 spectrogram kernel: SP_FAST=r64 (default: the 64 x 64 kernel, 16-frame tiles) or SP_FAST=dbx (the
+// 16 x 16 x 16 kernel, 8-frame tiles); SP_NO_FAST disables both.
+static bool use_r64()
+{
+    static const char *v = getenv("SP_FAST");
+    return !(v && !strcmp(v, "dbx"));
+}
 struct Plan {
     int log2k = 0;       // kernel FFT size (log2)
     int sub_r = 1;       // pre-pass radix (n = sub_r * 4096 when > 1)
@@ -320,7 +347,10 @@ extern "C" const char *sp_kernel_plan(sp_engine *e, int format, int n, int chann
              specialised(format) ? k_names[format] : "runtime-format", pl.tile, pl.smem_x * 8, channel_mode ? " +splitreal" : "");
     if (pl.log2k == 12 && !channel_mode && !getenv("SP_NO_FAST")) {
         const size_t l = strlen(buf);
-        snprintf(buf + l, sizeof buf - l, " | spectrogram fast path: render_fast_kernel<slots=2,frames=8> (TMA-staged input, packed fp32)");
+        if (use_r64() && (pl.sub_r > 1 ? sp_r64_cf32 != nullptr : r64_for(format) != nullptr) && (pl.sub_r > 1 || sp::sample_width(format) <= 8))
+            snprintf(buf + l, sizeof buf - l, " | spectrogram fast path: render_r64_kernel<streams=4,tile=16 frames> (64x64 FFT, one exchange, joint histogram, TMA-staged input)");
+        else
+            snprintf(buf + l, sizeof buf - l, " | spectrogram fast path: render_fast_kernel<slots=2,frames=8> (TMA-staged input, packed fp32)");
     }
     e->plan = buf;
     return e->plan.c_str();
@@ -472,6 +502,13 @@ static int prepare(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, boo
     p.gc = (float)((double)(rq->cmap_len - 1) - rq->gain * color_norm);
     p.cmaxf = (float)(rq->cmap_len - 1);
     p.cmap_len = rq->cmap_len;
+    {   // joint-histogram constants (sp_kernels.cuh, jh_eval): in double, rounded once
+        const double c1 = 5.0 * log10(2.0), cmaxd = (double)(rq->cmap_len - 1);
+        p.jA = (float)(-10.0 * c1 / sp::JH_RCAP);
+        p.jB = (float)((2.0 - 10.0 * block_norm_db) / sp::JH_RCAP);
+        p.jC = (float)(-color_norm * c1 / cmaxd);
+        p.jD = (float)((cmaxd - (block_norm_db + rq->gain) * color_norm) / cmaxd);
+    }
     p.waterfall = rq->waterfall ? 1 : 0;
     p.channel_mode = rq->channel_mode ? 1 : 0;
     p.sub_r = j.plan.sub_r;
@@ -495,7 +532,8 @@ static int prepare(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, boo
     p.fmax = (float *)e->fmax.p;
     p.fmid = (float2 *)e->fmid.p;
     if ((rc = ensure(e, e->hist, 8 * (size_t)(SP_CB_HIST_SIZE + SP_MAX_CMAP)))) return rc;
-    if ((rc = ensure(e, e->stats, 16)) || (rc = ensure(e, e->mm, 16))) return rc;
+    if ((rc = ensure(e, e->stats, 16)) || (rc = ensure(e, e->mm, 16)) || (rc = ensure(e, e->jhist, 8 * (size_t)sp::JH_SIZE))) return rc;
+    p.j_hist = (unsigned long long *)e->jhist.p;
     if ((rc = ensure(e, e->gauges, 3 * W))) return rc;
     if (out_dev) {
         j.d_cb = rp->cB_hist ? (unsigned long long *)rp->cB_hist : (unsigned long long *)e->hist.p;
@@ -561,6 +599,45 @@ static int launch_fast_kernel(sp_engine *e, fast_fn fn, Params &q, long long *nf
     return SP_OK;
 }
 
+// Frames [0, *nfast) of the chunk described by q go through render_r64_kernel: whole tiles of 16 frames inside the buffer.
+static int launch_r64_kernel(sp_engine *e, r64_fn fn, Params &q, long long *nfast)
+{
+    const bool sub = q.sub_r > 1;
+    long long nf = q.chunk_frames / 16 * 16;
+    if (!sub) {
+        const long long sw = sp::sample_width(q.format);
+        auto inside = [&](long long xr) {
+            const long long xgl = q.frame_first + q.chunk_first + xr;
+            const long long p0 = (long long)(0.5 + q.stride * (double)xgl) - q.sample_base;       // lib/worker.js:72
+            // the bulk copy reads whole 16-byte units: keep the rounded-up end inside the buffer's readable slack
+            return p0 >= 0 && (unsigned long long)(p0 + 4096) * (unsigned long long)sw <= q.valid_bytes;
+        };
+        while (nf > 0 && !inside(nf - 1)) nf -= 16;
+        if (nf > 0 && !inside(0)) nf = 0;
+    }
+    *nfast = nf;
+    if (nf == 0) return SP_OK;
+    const float2 *tw14 = nullptr;
+    int rc = get_r64_table(e, &tw14), occ = 0;
+    if (rc) return rc;
+    CU(fn(sub ? 1 : 0, &q, 0, e->stream, nullptr, tw14, &occ));
+    if (occ < 1) { *nfast = 0; return SP_OK; }             // not built for this format: the caller falls back
+    if (e->ctr_next == sp::TILE_COUNTERS) {
+        CU(cudaMemsetAsync(e->tilectr.p, 0, 4 * sp::TILE_COUNTERS, e->stream));
+        e->ctr_next = 0;
+    }
+    unsigned *ctr = (unsigned *)e->tilectr.p + e->ctr_next++;
+    Params r = q;
+    r.chunk_frames = nf;
+    r.ntiles = (nf / 16) * (sub ? q.sub_r : 1);
+    const int grid = (int)(r.ntiles < e->sm_count ? r.ntiles : e->sm_count);
+    prof_begin(e);
+    CU(fn(sub ? 1 : 0, &r, grid, e->stream, ctr, tw14, nullptr));
+    prof_end(e);
+    e->launches++;
+    return SP_OK;
+}
+
 // Enqueue all kernels of a job on e->stream (bracketed by the timing events).
 static int enqueue_begin(sp_engine *e, Job &j)
 {
@@ -568,7 +645,8 @@ static int enqueue_begin(sp_engine *e, Job &j)
     int rc = ensure(e, e->tilectr, 4 * sp::TILE_COUNTERS);
     if (rc) return rc;
     CU(cudaEventRecord(e->ev0, e->stream));
-    sp::prep_kernel<<<(SP_MAX_CMAP + 255) / 256, 256, 0, e->stream>>>(j.d_cb, j.d_c, j.p.cmap_len, (unsigned *)e->tilectr.p, (unsigned *)e->mm.p);
+    sp::prep_kernel<<<(SP_MAX_CMAP + 255) / 256, 256, 0, e->stream>>>(j.d_cb, j.d_c, j.p.cmap_len, (unsigned *)e->tilectr.p, (unsigned *)e->mm.p,
+                                                                          (unsigned long long *)e->jhist.p);
     e->ctr_next = 0;
     e->launches++;
     return SP_OK;
@@ -582,7 +660,14 @@ static int enqueue_frames(sp_engine *e, Job &j, Params &p)
     int occ = 0;
     if (j.plan.sub_r == 1) {
         Params q = p;
-        if (j.plan.log2k == 12 && fast_eligible(p) && fast_for(fmt)) {
+        if (j.plan.log2k == 12 && fast_eligible(p) && use_r64() && r64_for(fmt) && (q.chunk_first % 16 == 0)) {
+            long long nfast = 0;
+            int rc = launch_r64_kernel(e, r64_for(fmt), q, &nfast);
+            if (rc) return rc;
+            q.chunk_first += nfast;
+            q.chunk_frames -= nfast;
+        }
+        if (j.plan.log2k == 12 && fast_eligible(q) && fast_for(fmt) && q.chunk_frames >= 8) {
             long long nfast = 0;
             int rc = launch_fast_kernel(e, fast_for(fmt), q, &nfast);
             if (rc) return rc;
@@ -641,7 +726,14 @@ static int enqueue_frames(sp_engine *e, Job &j, Params &p)
             e->launches++;
             Params full = q;                                   // what the epilogue kernel sees
             if (tap) { q.spec_out = (float2 *)e->spec.p; q.image = nullptr; q.db_out = nullptr; q.channel_mode = 0; }
-            if (fast_eligible(q) && ff) {
+            if (fast_eligible(q) && use_r64() && sp_r64_cf32 && (q.chunk_first % 16 == 0)) {
+                long long nfast = 0;
+                if ((rc = launch_r64_kernel(e, sp_r64_cf32, q, &nfast))) return rc;
+                q.sub_in += (size_t)nfast * (size_t)R * 4096;
+                q.chunk_first += nfast;
+                q.chunk_frames -= nfast;
+            }
+            if (fast_eligible(q) && ff && q.chunk_frames >= 8) {
                 long long nfast = 0;
                 if ((rc = launch_fast_kernel(e, ff, q, &nfast))) return rc;
                 q.sub_in += (size_t)nfast * (size_t)R * 4096;
@@ -674,7 +766,7 @@ static int enqueue_end(sp_engine *e, Job &j)
     Params &p = j.p;
     sp::finalize_kernel<<<(unsigned)((p.nframes + 255) / 256), 256, 0, e->stream>>>(
         p.fmin, p.fmax, p.fmid, p.nframes, j.range, j.gain, j.plan.sub_r > 1 ? 1 : 0, j.d_gmin, j.d_gmax, j.d_gamp,
-        (unsigned *)e->mm.p, j.d_stats);
+        (unsigned *)e->mm.p, j.d_stats, (const unsigned long long *)e->jhist.p, sp::jh_const(p), p.cmap_len, j.d_cb, j.d_c);
     e->launches++;
     CU(cudaGetLastError());
     CU(cudaEventRecord(e->ev1, e->stream));

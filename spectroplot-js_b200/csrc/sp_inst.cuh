@@ -5,6 +5,7 @@
 #pragma once
 #include "sp_kernels.cuh"
 #include "sp_kernel_fast.cuh"
+#include "sp_kernel_r64.cuh"
 
 namespace sp {
 
@@ -84,6 +85,33 @@ static cudaError_t launch_fast_v(const Params &p, int grid, cudaStream_t st, uns
     return cudaGetLastError();
 }
 
+// N = 4096 "64 x 64" path: one CTA of 4 x 64 threads per SM, 16 frames per tile (sp_kernel_r64.cuh).
+template <int FMT, bool SUB>
+static cudaError_t launch_r64_v(const Params &p, int grid, cudaStream_t st, unsigned *tile_counter, const float2 *tw14, int *occ_out)
+{
+    using B = R64Cfg<FMT, SUB>;
+    if constexpr (!B::OK) {
+        if (occ_out) *occ_out = 0;
+        return occ_out ? cudaSuccess : cudaErrorInvalidValue;
+    } else {
+        auto kfn = render_r64_kernel<FMT, SUB>;
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+            attr_done = true;
+        }
+        if (occ_out) {
+            int nb = 0;
+            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, B::THREADS, B::SMEM_BYTES);
+            *occ_out = nb;
+            return e;
+        }
+        kfn<<<grid, B::THREADS, B::SMEM_BYTES, st>>>(p, tw14, tile_counter);
+        return cudaGetLastError();
+    }
+}
+
 } // namespace sp
 
 #define SP_CAT2(a, b) a##b
@@ -103,6 +131,14 @@ extern "C" cudaError_t SP_CAT(sp_fl_, SP_INST_TAG)(int sub, const sp::Params *p,
         if (sub) return sp::launch_fast_v<SP_INST_FMT, true>(*p, grid, st, tile_counter, tw6A, tw6B, occ_out);
     } else if (sub) return cudaErrorInvalidValue;
     return sp::launch_fast_v<SP_INST_FMT, false>(*p, grid, st, tile_counter, tw6A, tw6B, occ_out);
+}
+extern "C" cudaError_t SP_CAT(sp_r64_, SP_INST_TAG)(int sub, const sp::Params *p, int grid, cudaStream_t st, unsigned *tile_counter,
+                                                     const float2 *tw14, int *occ_out)
+{
+    if constexpr (SP_INST_FMT == sp::CF32 || SP_INST_FMT == sp::FMT_RUNTIME) {
+        if (sub) return sp::launch_r64_v<SP_INST_FMT, true>(*p, grid, st, tile_counter, tw14, occ_out);
+    } else if (sub) return cudaErrorInvalidValue;
+    return sp::launch_r64_v<SP_INST_FMT, false>(*p, grid, st, tile_counter, tw14, occ_out);
 }
 extern "C" cudaError_t SP_CAT(sp_pl_, SP_INST_TAG)(int r, const sp::Params *p, float2 *out, const float2 *tw_full,
                                                     cudaStream_t st)

@@ -90,6 +90,11 @@ __device__ __forceinline__ void red_shared_inc(unsigned *p)
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(smem_u32(p)) : "memory");
 }
 
+__device__ __forceinline__ void red_shared_inc_addr(unsigned addr)
+{
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+}
+
 // v[k] *= w^k, k = 1..15, from the six table entries tw[0..5] = w^1 w^2 w^3 w^4 w^8 w^12
 __device__ __forceinline__ void twiddle16_from6(cf (&v)[16], const float4 t01, const float4 t23, const float4 t45)
 {

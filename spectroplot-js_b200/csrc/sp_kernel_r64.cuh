@@ -1,0 +1,320 @@
+// sp_kernel_r64.cuh — the N = 4096 "64 x 64" render kernel: the headline size, and the second stage of
+// the four-step path for N = 8192..65536.
+//
+// Why another N = 4096 kernel: ncu on the 16 x 16 x 16 kernel (profiles/r01_ncu_summary_s4a_dbx.txt)
+// shows the L1/shared-memory data pipe as the binding unit (22.5 wavefronts per 32 samples: two
+// exchanges = 8, two histogram atomics = 3.6, window + twiddle tables = 2.5, scattered 32-byte row
+// stores = 4.3, ...).  This kernel is built around that number:
+//   * 4096 = 64 x 64: a thread holds 64 complex points, a frame is transformed by 64 threads with
+//     ONE shared-memory exchange (4 wavefronts per 32 samples instead of 8), read back with LDS.128;
+//   * ONE histogram atomic per pixel: the dB bin r and the colour index g are both monotone in
+//     log2|X|^2, so the joint index r + (cmax - g) determines the pair; it is formed by FFMA.SAT +
+//     FFMA on a 2^23 "magic" bias (no F2I, no integer clamps) and decoded once per render by
+//     finalize_kernel (jh_decode);
+//   * colour indices are staged as bytes in shared memory for a tile of 16 consecutive frames, so the
+//     transposed image store (lib/worker.js:117) writes 64 contiguous bytes per row from two lanes
+//     (half the L1 wavefronts of the 32-byte segments of the older kernels) and needs no registers;
+//   * four independent frame streams per CTA (64 threads = 2 warps each, named barriers), one
+//     persistent CTA per SM; the raw bytes of a stream's next frame are prefetched by one TMA bulk
+//     copy INTO the stream's exchange buffer while the current frame is in registers.
+// Only full tiles of frames that lie inside the buffer come here (spectrogram layout, cmap_len <= 256);
+// the engine routes everything else through render_kernel.
+// Replaces the hot loops of reference lib/worker.js:68-137 (+ lib/samples.js:313-400,
+// lib/fft_nayuki.js:54-96).
+#pragma once
+#include "sp_kernel_fast.cuh"
+
+namespace sp {
+
+template <int FMT, bool SUB> struct R64Cfg {
+    static constexpr int N = 4096, T = 64, STREAMS = 4, THREADS = T * STREAMS, STEPS = 4, F = STREAMS * STEPS;   // 16 frames per tile
+    static constexpr int SWB = SUB ? 8 : sample_width(FMT == FMT_RUNTIME ? CF64 : FMT);
+    static constexpr bool OK = SUB || ((FMT != FMT_RUNTIME) && SWB <= 8);       // raw frame fits the exchange buffer
+    static constexpr int XP = 66;                                                // exchange row pitch (float2): LDS.128 conflict-free
+    static constexpr int X_BYTES = 64 * XP * 8;                                  // 33 792 >= 4096 * 8 + 32
+    static constexpr int WIN_PITCH = 64;                                         // floats per thread row, rotated by 4*t (conflict-free LDS.128)
+    static constexpr int TW_PITCH = 14;                                          // float2 per thread row: w^1..w^7, w^8, w^16 .. w^56
+    static constexpr int ST_PITCH = 1026;                                        // staging words per frame (1024 used)
+    static constexpr size_t SMEM_BYTES = (size_t)STREAMS * X_BYTES + (size_t)F * ST_PITCH * 4 + (size_t)JH_SIZE * 4
+                                       + (SUB ? 0 : (size_t)T * WIN_PITCH * 4) + (size_t)T * TW_PITCH * 8 + 1024 /* LUT */
+                                       + (size_t)F * 2 * 8 + 128 + 1024 /* LUT alignment */;
+};
+
+// RGBA of byte j of a staged word: table base on a 1 KB boundary of the shared window
+__device__ __forceinline__ unsigned lut_at(unsigned lut_base, unsigned word, int j)
+{
+    const unsigned a = ((j == 0 ? word << 2 : word >> (8 * j - 2)) & 0x3fcu) | lut_base;
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
+__device__ __forceinline__ void stream_barrier(int stream)
+{
+    asm volatile("bar.sync %0, 64;" ::"r"(stream + 1) : "memory");
+}
+
+// tw14: [64][14] float2 = W_4096^{t*k}, k = 1..7, 8, 16, 24, 32, 40, 48, 56
+template <int FMT, bool SUB>
+__global__ void __launch_bounds__(256, 1) render_r64_kernel(const Params p, const float2 *__restrict__ tw14,
+                                                            unsigned *__restrict__ tile_counter)
+{
+    using B = R64Cfg<FMT, SUB>;
+    constexpr int N = B::N, T = B::T, F = B::F;
+    constexpr bool FLOAT_IN = SUB || FMT == CF32 || FMT == CF64 || FMT == FMT_RUNTIME;   // |X|^2 may be +inf / NaN
+    extern __shared__ __align__(128) unsigned char smem_r64[];
+    // the reversed RGBA LUT sits on a 1 KB boundary of the shared window so that a pixel's table address is
+    // ((word >> shift) & 0x3fc) | lut_base: one SHF + one 3-input LOP3 per lookup
+    const unsigned lut_base = (smem_u32(smem_r64) + 1023u) & ~1023u;
+    unsigned char *s_x = smem_r64 + (lut_base - smem_u32(smem_r64)) + 1024;           // [4][X_BYTES] exchange / raw frame
+    unsigned *s_lut = reinterpret_cast<unsigned *>(s_x - 1024);                       // [256] RGBA, REVERSED (index cmax - g)
+    unsigned *s_stage = reinterpret_cast<unsigned *>(s_x + B::STREAMS * B::X_BYTES);  // [16][1026] colour bytes (4 bins per word)
+    unsigned *s_jh = s_stage + F * B::ST_PITCH;                                       // [JH_SIZE] joint histogram
+    float *s_win = reinterpret_cast<float *>(s_jh + JH_SIZE);                         // [64][64] (row t: window[64 a + t] at (a + 4t) mod 64)
+    float2 *s_tw = reinterpret_cast<float2 *>(s_win + (SUB ? 0 : T * B::WIN_PITCH));  // [64][14]
+    uint2 *s_mm = reinterpret_cast<uint2 *>(s_tw + T * B::TW_PITCH);                  // [16][2] per-warp min/max bit patterns of |X|^2
+    uint64_t *s_mbar = reinterpret_cast<uint64_t *>(s_mm + F * 2);                    // [4]
+    int *s_off = reinterpret_cast<int *>(s_mbar + B::STREAMS);                        // [4][2] misalignment of the staged frame
+    unsigned *s_tile = reinterpret_cast<unsigned *>(s_off + B::STREAMS * 2);          // [2] tile ring
+
+    const int tid = threadIdx.x;
+    const int s = tid >> 6;                 // stream
+    const int t = tid & 63;
+    float2 *X = reinterpret_cast<float2 *>(s_x + (size_t)s * B::X_BYTES);
+    unsigned char *raw = reinterpret_cast<unsigned char *>(X);
+    uint64_t *mbar = s_mbar + s;
+
+    for (int i = tid; i < JH_SIZE; i += B::THREADS) s_jh[i] = 0;
+    const int cmax = p.cmap_len - 1;
+    for (int i = tid; i < 256; i += B::THREADS) s_lut[i] = i <= cmax ? p.lut[cmax - i] : 0u;
+    for (int i = tid; i < T * B::TW_PITCH; i += B::THREADS) s_tw[i] = tw14[i];
+    if constexpr (!SUB)
+        for (int i = tid; i < N; i += B::THREADS) s_win[(i & 63) * B::WIN_PITCH + (((i >> 6) + 4 * (i & 63)) & 63)] = p.window[i];
+    const JhConst jc = jh_const(p);
+    const unsigned jh_base = smem_u32(s_jh) - (JH_MAGIC_BITS << 2);      // address of joint bin j = S.bits * 4 + jh_base (mod 2^32)
+    const int nfull = p.n_full, sub_r = p.sub_r;
+
+    // t == 0 of a stream: start the bulk copy of chunk-relative frame xr (sub-sequence k0sub) into the stream's buffer
+    auto stage = [&](long long xr, int k0sub, unsigned par) {
+        const void *src;
+        unsigned bytes;
+        if constexpr (SUB) {
+            src = p.sub_in + ((size_t)xr * sub_r + (size_t)k0sub) * N;
+            bytes = N * 8;
+            s_off[s * 2 + par] = 0;
+        } else {
+            const long long xgl = p.frame_first + p.chunk_first + xr;
+            const long long p0 = (long long)__dadd_rn(0.5, __dmul_rn(p.stride, (double)xgl)) - p.sample_base;   // lib/worker.js:72
+            const unsigned long long off = (unsigned long long)p0 * B::SWB, a0 = off & ~15ull;
+            src = p.buf + a0;
+            bytes = (unsigned)(((off - a0) + (unsigned long long)N * B::SWB + 15) & ~15ull);
+            s_off[s * 2 + par] = (int)(off - a0);
+        }
+        tma_load_1d(raw, src, bytes, mbar);
+    };
+    // tile -> first chunk-relative frame, sub-sequence
+    auto tile_xr0 = [&](long long tile) -> long long { return (SUB ? tile / sub_r : tile) * F; };
+
+    if (tid == 0) {
+        s_tile[0] = atomicAdd(tile_counter, 1u);
+        s_tile[1] = atomicAdd(tile_counter, 1u);
+    }
+    if (t == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    long long tile = s_tile[0], next_tile = s_tile[1];
+    int ring = 0;
+    unsigned fpar = 0;                      // parity of this stream's frame counter (mbarrier phase, s_off slot)
+    if (t == 0 && tile < p.ntiles) stage(tile_xr0(tile) + s, SUB ? (int)(tile % sub_r) : 0, 0);
+
+    while (tile < p.ntiles) {
+        const int k0sub = SUB ? (int)(tile % sub_r) : 0;
+        const long long xr0 = tile_xr0(tile);
+        if (tid == 0) s_tile[ring] = atomicAdd(tile_counter, 1u);       // the tile after next (read after the tile barrier)
+
+#pragma unroll 1
+        for (int step = 0; step < B::STEPS; step++) {
+            const int fl = step * B::STREAMS + s;                       // frame of the tile handled by this stream now
+            cf v[64];
+            // ---------------- load + decode + window (lib/worker.js:70-75) ----------------
+            mbar_wait(mbar, fpar);
+            if constexpr (SUB) {
+#pragma unroll
+                for (int a = 0; a < 64; a++) v[a] = cld(reinterpret_cast<const float2 *>(raw) + T * a + t);
+            } else {
+                const unsigned char *rp = raw + s_off[s * 2 + fpar];
+#pragma unroll
+                for (int a = 0; a < 64; a++) v[a] = cpk(decode_raw<FMT>(rp, T * a + t, p.format));
+                // raw sample at p0 + n/2 (lib/worker.js:131-133); the power-of-two scale is exact
+                if (t == 0) p.fmid[p.chunk_first + xr0 + fl] = make_float2(cre(v[32]) * raw_scale<FMT>(), cim(v[32]) * raw_scale<FMT>());
+                const float4 *wrow = reinterpret_cast<const float4 *>(s_win + t * B::WIN_PITCH);
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    const float4 w = wrow[(q + t) & 15];
+                    v[4 * q] = cscale(v[4 * q], w.x);         v[4 * q + 1] = cscale(v[4 * q + 1], w.y);
+                    v[4 * q + 2] = cscale(v[4 * q + 2], w.z); v[4 * q + 3] = cscale(v[4 * q + 3], w.w);
+                }
+            }
+            fpar ^= 1;
+
+            // ---------------- pass A: DFT-64 over the slow input digit, twiddle W_4096^{t*k0} ----------------
+            dft<64>(v);
+            {
+                const float4 *twp = reinterpret_cast<const float4 *>(s_tw + t * B::TW_PITCH);
+                float2 w[8];                                            // w[j] = W^{t*j}, j = 1..7
+                {
+                    const float4 a = twp[0], b = twp[1], c = twp[2], d = twp[3];
+                    w[1] = make_float2(a.x, a.y); w[2] = make_float2(a.z, a.w); w[3] = make_float2(b.x, b.y); w[4] = make_float2(b.z, b.w);
+                    w[5] = make_float2(c.x, c.y); w[6] = make_float2(c.z, c.w); w[7] = make_float2(d.x, d.y);
+#pragma unroll
+                    for (int j = 1; j < 8; j++) v[j] = cmul(v[j], w[j]);
+                    float2 hi[8];                                       // hi[i] = W^{t*8i}, i = 1..7
+                    hi[1] = make_float2(d.z, d.w);
+                    const float4 e = twp[4], f = twp[5], g = twp[6];
+                    hi[2] = make_float2(e.x, e.y); hi[3] = make_float2(e.z, e.w); hi[4] = make_float2(f.x, f.y);
+                    hi[5] = make_float2(f.z, f.w); hi[6] = make_float2(g.x, g.y); hi[7] = make_float2(g.z, g.w);
+#pragma unroll
+                    for (int i = 1; i < 8; i++) {
+                        v[8 * i] = cmul(v[8 * i], hi[i]);
+#pragma unroll
+                        for (int j = 1; j < 8; j++) v[8 * i + j] = cmul(v[8 * i + j], cun(cmul(cpk(hi[i]), w[j])));
+                    }
+                }
+            }
+            stream_barrier(s);                                          // every thread of the stream has consumed the raw frame
+#pragma unroll
+            for (int k = 0; k < 64; k++) cst(X + k * B::XP + t, v[k]);  // Z[k0][t]
+            stream_barrier(s);
+            // ---------------- pass B: thread k0 = t, DFT-64 over b ----------------
+            {
+                const float4 *row = reinterpret_cast<const float4 *>(X + t * B::XP);
+#pragma unroll
+                for (int m = 0; m < 32; m++) {
+                    const float4 q = row[m];
+                    v[2 * m] = cpk(q.x, q.y); v[2 * m + 1] = cpk(q.z, q.w);
+                }
+            }
+            stream_barrier(s);                                          // the exchange buffer is free: prefetch the stream's next frame
+            if (t == 0) {
+                if (step < B::STEPS - 1) stage(xr0 + fl + B::STREAMS, k0sub, fpar);
+                else if (next_tile < p.ntiles) stage(tile_xr0(next_tile) + s, SUB ? (int)(next_tile % sub_r) : 0, fpar);
+            }
+            dft<64>(v);                                                 // v[k1] is bin t + 64*k1
+
+            // ---------------- per-bin epilogue (lib/worker.js:85-122) ----------------
+            float amin = __int_as_float(0x7f800000), amax = 0.0f, prev = 0.0f;
+            unsigned umin_i = 0x7f800000u, umax_i = 0u;
+            unsigned *stg = s_stage + fl * B::ST_PITCH + t;
+#pragma unroll
+            for (int m = 0; m < 16; m++) {
+                unsigned yb[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float2 vi = cun(v[4 * m + j]);
+                    const float abs2 = fmaf(vi.x, vi.x, vi.y * vi.y);
+                    if constexpr (FLOAT_IN) {
+                        // unsigned order on the bit patterns: a NaN wins the max (and is sorted out below), never the min
+                        umin_i = min(umin_i, __float_as_uint(abs2));
+                        umax_i = max(umax_i, __float_as_uint(abs2));
+                    } else if (j & 1) {                          // 3-input min / max: one FMNMX3 per two bins
+                        amin = fmin3(amin, prev, abs2);
+                        amax = fmax3(amax, prev, abs2);
+                    } else prev = abs2;
+                    const float l2 = fast_log2(abs2);
+                    float Y;
+                    const float S = jh_eval(l2, jc, Y);          // 2^23 + joint index, 2^23 + (cmax - colour index)
+                    red_shared_inc_addr(jh_base + (__float_as_uint(S) << 2));
+                    yb[j] = __float_as_uint(Y);
+                }
+                // bins t + 64*(4m .. 4m+3) of frame fl: four colour bytes in one word
+                stg[m * 64] = __byte_perm(__byte_perm(yb[0], yb[1], 0x0040), __byte_perm(yb[2], yb[3], 0x0040), 0x5410);
+            }
+            unsigned umn, umx;
+            if constexpr (FLOAT_IN) {
+                umn = __reduce_min_sync(0xffffffffu, umin_i);
+                umx = __reduce_max_sync(0xffffffffu, umax_i);
+            } else {
+                // |X|^2 >= 0: the bit patterns order like the values
+                umn = __reduce_min_sync(0xffffffffu, __float_as_uint(amin));
+                umx = __reduce_max_sync(0xffffffffu, __float_as_uint(amax));
+            }
+            if (umn < 0x00800000u || umx >= 0x7f800000u) {
+                // rare (warp-uniform): the frame holds |X|^2 == 0 (flushed: d0 = -inf), +inf or NaN.  Count them for
+                // the bin-0 fix-ups (lib/worker.js:105-106: ~~(+-Infinity) == ~~NaN == 0) and redo min / max the way
+                // the reference's `<` / `>` see them (NaN never wins).
+                unsigned nzero = 0, nbad = 0;
+                float mn = __int_as_float(0x7f800000), mx = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 64; i++) {
+                    const float2 vi = cun(v[i]);
+                    const float abs2 = fmaf(vi.x, vi.x, vi.y * vi.y);
+                    nzero += abs2 < 1.17549435e-38f ? 1u : 0u;
+                    nbad += !(abs2 <= 3.402823466e38f) ? 1u : 0u;
+                    mn = fminf(mn, abs2 < 1.17549435e-38f ? 0.0f : abs2);
+                    mx = fmaxf(mx, abs2);
+                }
+                nzero = __reduce_add_sync(0xffffffffu, nzero);
+                nbad = __reduce_add_sync(0xffffffffu, nbad);
+                umn = __reduce_min_sync(0xffffffffu, __float_as_uint(mn));
+                umx = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+                if ((t & 31) == 0) {
+                    if (nzero) atomicAdd(&s_jh[JH_ZERO], nzero);
+                    if (nbad) atomicAdd(&s_jh[JH_BAD], nbad);
+                }
+            }
+            if ((t & 31) == 0) s_mm[fl * 2 + (t >> 5)] = make_uint2(umn, umx);
+        } // steps
+
+        __syncthreads();                    // the tile's 16 frames are staged; s_mm and s_tile[ring] are written
+
+        // ---------------- row stores: 2 lanes x 8 frames x RGBA = 64 contiguous bytes per bin (lib/worker.js:117) ----------------
+        {
+            const size_t x0 = (size_t)(p.chunk_first + xr0);
+#pragma unroll 1
+            for (int it = 0; it < 8; it++) {
+                const int id = tid + B::THREADS * it;
+                const int half = id & 1, q = id >> 1, k0 = q & 63, m = q >> 6;
+                const unsigned *src = s_stage + (8 * half) * B::ST_PITCH + m * 64 + k0;
+                unsigned w[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) w[i] = src[i * B::ST_PITCH];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int kk = k0 + 64 * (4 * m + j);
+                    const int bin = SUB ? k0sub + sub_r * kk : kk;
+                    const int y = (nfull / 2 - bin) & (nfull - 1);                             // lib/worker.js:90
+                    uint32_t *rowp = reinterpret_cast<uint32_t *>(p.image) + (size_t)p.nframes * (size_t)y + x0 + 8 * half;
+                    uint4 a, b;
+                    a.x = lut_at(lut_base, w[0], j); a.y = lut_at(lut_base, w[1], j); a.z = lut_at(lut_base, w[2], j); a.w = lut_at(lut_base, w[3], j);
+                    b.x = lut_at(lut_base, w[4], j); b.y = lut_at(lut_base, w[5], j); b.z = lut_at(lut_base, w[6], j); b.w = lut_at(lut_base, w[7], j);
+                    st_global_256(rowp, a, b);
+                }
+            }
+            // per-frame min / max of the tile, folded across the stream's two warps and converted to dB
+            if (tid < F) {
+                const long long xl = p.chunk_first + xr0 + tid;
+                const uint2 m0 = s_mm[tid * 2], m1 = s_mm[tid * 2 + 1];
+                const unsigned umn = min(m0.x, m1.x), umx = max(m0.y, m1.y);
+                const float mn = fminf(0.0f, fmaf(fast_log2(__uint_as_float(umn)), p.c1, p.c0));       // lib/worker.js:82,102
+                const float mx = fmaxf(-200.0f, fmaf(fast_log2(__uint_as_float(umx)), p.c1, p.c0));    // lib/worker.js:83,103
+                if constexpr (SUB) {
+                    atomicMin(reinterpret_cast<unsigned *>(p.fmin) + xl, f2ord(mn));
+                    atomicMax(reinterpret_cast<unsigned *>(p.fmax) + xl, f2ord(mx));
+                } else { p.fmin[xl] = mn; p.fmax[xl] = mx; }
+            }
+        }
+        const unsigned fetched = s_tile[ring];
+        __syncthreads();                    // staging, s_mm and the tile ring may be rewritten
+        tile = next_tile;
+        next_tile = fetched;
+        ring ^= 1;
+    } // tiles
+
+    __syncthreads();
+    for (int i = tid; i < JH_SIZE; i += B::THREADS)
+        if (s_jh[i]) atomicAdd(&p.j_hist[i], (unsigned long long)s_jh[i]);
+}
+
+} // namespace sp

@@ -52,6 +52,9 @@ struct Params {
     long long chunk_first;         // first local frame of this launch (multiple of 8)
     long long chunk_frames;        // frames rendered by this launch (== nframes when not chunked)
     long long ntiles;
+    // joint (dB bin, colour index) histogram of render_r64_kernel (decoded by finalize_kernel)
+    unsigned long long *j_hist;    // [JH_SIZE]
+    float jA, jB, jC, jD;          // see jh_eval()
 };
 
 template <int LOG2N> struct Cfg {
@@ -94,6 +97,44 @@ __host__ __device__ inline size_t main_smem_bytes(int smem_x_float2, int cmap_le
     return (size_t)smem_x_float2 * 8 + (size_t)CB_RAW * 4 + (size_t)cmap_len * 8 + 64 * 8 + (size_t)twb_float2 * 8;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Joint histogram (render_r64_kernel).  Per pixel, with l2 = log2|X|^2 and d0 = c1*l2 + c0 (= dBfs - gain):
+//   r  = RN(sat(jA*l2 + jB) * RCAP),  jA*l2 + jB = (2.0 - 10*d0) / RCAP   : RN(x - 0.5) == trunc(x) for the
+//        x = 2.5 - 10*d0 of the table above (off quantisation ties), saturating at 0 and RCAP = 1003
+//   g' = RN(sat(jC*l2 + jD) * cmax) subtracted from cmax, jC*l2 + jD = (cmax - (d0 + gain)*color_norm) / cmax
+//        (lib/worker.js:111-112: the colour index g = cmax - g', clamped by the saturation)
+// Both roundings are done by adding 2^23 inside an FFMA, so S = 2^23 + r + g' and Y = 2^23 + g' come out of
+// four FMA-pipe instructions with no F2I and no integer clamp.  r falls and g rises with l2, so j = r + g'
+// is monotone and (r, g') is a function of j: ONE shared-memory atomic per pixel.  jh_decode() inverts j
+// by bisection over the ordered floats with the SAME jh_eval().  Non-finite pixels (|X|^2 flushed to 0,
+// +inf, NaN) take the ordinary path and are corrected per frame through two extra counters:
+//   JH_ZERO  pixels with d0 = -inf: counted as r = RCAP (bin 999) -> move them to bin 0  (~~(+Infinity) == 0)
+//   JH_BAD   pixels with d0 = +inf or NaN: counted as r = 0 (dropped) -> add them to bin 0
+// ---------------------------------------------------------------------------------------------
+constexpr int JH_RCAP = 1003;
+constexpr int JH_BINS = JH_RCAP + 1 + 256;
+constexpr int JH_ZERO = JH_BINS, JH_BAD = JH_BINS + 1, JH_SIZE = JH_BINS + 4;
+constexpr unsigned JH_MAGIC_BITS = 0x4B000000u;       // 2^23
+
+struct JhConst { float A, B, C, D, rcap, ncmax, ymagic; };
+__host__ __device__ __forceinline__ JhConst jh_const(const Params &p)
+{
+    JhConst c;
+    c.A = p.jA; c.B = p.jB; c.C = p.jC; c.D = p.jD;
+    c.rcap = (float)JH_RCAP;
+    c.ncmax = -(float)(p.cmap_len - 1);
+    c.ymagic = (float)(p.cmap_len - 1) + 8388608.0f;
+    return c;
+}
+// returns S = 2^23 + r + g'; Y = 2^23 + g'
+__device__ __forceinline__ float jh_eval(float l2, const JhConst &c, float &Y)
+{
+    const float kx = __saturatef(fmaf(l2, c.A, c.B));
+    const float ky = __saturatef(fmaf(l2, c.C, c.D));
+    Y = fmaf(ky, c.ncmax, c.ymagic);
+    return fmaf(kx, c.rcap, Y);
+}
+
 __device__ __forceinline__ int cb_bin_of_raw(int r)
 {
     return r == 0 ? -1 : (r <= 2 ? 0 : (r <= 1001 ? r - 2 : (r < CB_RAW_CAP ? CB_BINS - 1 : 0)));
@@ -116,6 +157,24 @@ __device__ __forceinline__ unsigned f2ord(float f)
 __device__ __forceinline__ float ord2f(unsigned u)
 {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// joint index j -> (dB bin or -1, colour index); false when no log2|X|^2 maps to j
+__device__ inline bool jh_decode(int j, const JhConst &c, int cmax, int &bin, int &g)
+{
+    unsigned lo = f2ord(__int_as_float(0xff800000)), hi = f2ord(__int_as_float(0x7f800000));   // -inf .. +inf, no NaN between
+    float Y;
+    while (lo < hi) {                                  // smallest l2 with J(l2) <= j (J is non-increasing)
+        const unsigned mid = lo + (hi - lo) / 2;
+        const int J = (int)(__float_as_uint(jh_eval(ord2f(mid), c, Y)) - JH_MAGIC_BITS);
+        if (J <= j) hi = mid; else lo = mid + 1;
+    }
+    const int J = (int)(__float_as_uint(jh_eval(ord2f(lo), c, Y)) - JH_MAGIC_BITS);
+    const int gp = (int)(__float_as_uint(Y) - JH_MAGIC_BITS);
+    const int r = J - gp;
+    g = cmax - gp;
+    bin = r == 0 ? -1 : (r <= 2 ? 0 : (r <= 1001 ? r - 2 : CB_BINS - 1));
+    return J == j;
 }
 
 // shared-memory counters -> 64-bit global histograms (raw dB index mapped to the reference's bins)

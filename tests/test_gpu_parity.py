@@ -335,3 +335,80 @@ def test_zoom_levels_in_one_pass(engine):
         assert one["dBfs_min"] == o["dBfs_min"] and one["dBfs_max"] == o["dBfs_max"]
     ora = O.render(buf, fmt, n, widths[0], w, 1 / wt, 6, 30, CM256, taps=True)
     check_parity(outs[0], ora, CM256, n, widths[0], False, None, "zoom x1")
+
+
+# ------------------------------------------------------------------ the N = 4096 "64 x 64" kernel (render_r64_kernel)
+# Reached with spectrogram layout, cmap_len <= 256, width % 8 == 0 and at least 16 frames inside the buffer.
+@pytest.mark.parametrize("fmt", O.FORMATS)
+def test_r64_all_formats(engine, fmt):
+    n, width, hop = 4096, 48, 1501                       # overlapping frames at a fractional stride
+    S = hop * (width - 1) + n + 5
+    buf = O.synth(fmt, 0, S, S, 0x5EC7A000).tobytes()
+    gpu, ora, _ = run_both(engine, buf, fmt, n, width, "blackmanHarris", want_db=False)
+    if fmt in ("CU4", "CS4", "CU8", "CS8", "CU12", "CS12", "CU16", "CS16", "CF32"):      # formats with a specialised build
+        assert "render_r64_kernel" in engine.kernel_plan(fmt, n)
+
+
+@pytest.mark.parametrize("gain,rng,cmap_len", [(0, 60, 256), (-20, 5, 256), (6, 30, 64), (40, 100, 2), (6, -30, 256)])
+def test_r64_colour_scales(engine, gain, rng, cmap_len):
+    """The joint histogram index must decode for any gain / range / colormap length (lib/worker.js:37-39,111-113)."""
+    n, width = 4096, 32
+    S = n * width
+    buf = O.synth("CS16", 0, S, S, 0x5EC7A001).tobytes()
+    run_both(engine, buf, "CS16", n, width, "hann", gain=gain, rng=rng, cmap=injective_cmap(cmap_len), want_db=False)
+
+
+def test_r64_non_finite_pixels(engine):
+    """|X|^2 == 0, +inf and NaN take the per-frame fix-up path of the joint histogram (~~(+-Infinity) == ~~NaN == 0)."""
+    n, width = 4096, 32
+    w, wt = O.window("hann", n)
+    # every other group of frames silent: d0 = -inf -> bin 0, colour 0, min -inf
+    x = np.frombuffer(O.synth("CS16", 0, n * width, n * width, 0x5EC7A002).tobytes(), "<i2").reshape(width, n, 2).copy()
+    x[3:9] = 0
+    x[20] = 0
+    buf = x.tobytes()
+    ora = O.render(buf, "CS16", n, width, w, 1 / wt, 6, 30, CM256, taps=True)
+    gpu = engine.render(buf, "CS16", n, width, w, 1 / wt, 6, 30, CM256)
+    check_parity(gpu, ora, CM256, n, width, False, None, "r64 silent frames")
+    assert gpu["cB_hist"][0] >= 7 * n and gpu["dBfs_min"] == -np.inf
+    # float input with NaN, +inf and huge values (|X|^2 overflows to +inf)
+    f = np.frombuffer(O.synth("CF32", 0, n * width, n * width, 0x5EC7A003).tobytes(), "<f4").reshape(width, n, 2).copy()
+    f[2, 100, 0] = np.nan
+    f[5, 7, 1] = np.inf
+    f[9, :, :] *= np.float32(3e19)
+    f[11] = 0
+    buf = f.tobytes()
+    with np.errstate(all="ignore"):
+        ora = O.render(buf, "CF32", n, width, w, 1 / wt, 6, 30, CM256, taps=True)
+    gpu = engine.render(buf, "CF32", n, width, w, 1 / wt, 6, 30, CM256)
+    g = gray_from_image(gpu["image"], CM256, n, width)
+    for fr in (2, 5, 9, 11):
+        assert np.array_equal(g[fr], ora.gray[fr]), fr
+    assert int(np.abs(gpu["cB_hist"].astype(np.int64) - ora.cB_hist.astype(np.int64)).sum()) <= 64
+    assert int(np.abs(gpu["c_hist"].astype(np.int64) - ora.c_hist.astype(np.int64)).sum()) <= 64
+    assert gpu["dBfs_min"] == ora.dBfs_min and gpu["dBfs_max"] == ora.dBfs_max
+
+
+@pytest.mark.parametrize("n,width", [(8192, 32), (16384, 48), (32768, 16), (65536, 16)])
+def test_r64_four_step(engine, n, width):
+    S = n * width // 2 + n + 9                                 # ~50 % overlap
+    buf = O.synth("CS16", 0, S, S, 0x5EC7A100 + n).tobytes()
+    run_both(engine, buf, "CS16", n, width, "hann", want_db=False)
+
+
+def test_r64_matches_generic_kernel(engine):
+    """The same message through render_r64_kernel (spectrogram) and render_kernel (waterfall layout is not
+    eligible for the fast path): the two fp32 FFTs may only differ at quantisation ties."""
+    n, width = 4096, 64
+    S = n * width
+    buf = O.synth("CS16", 0, S, S, 0x5EC7A004).tobytes()
+    w, wt = O.window("blackmanHarris", n)
+    a = engine.render(buf, "CS16", n, width, w, 1 / wt, 0, 90, CM256)
+    b = engine.render(buf, "CS16", n, width, w, 1 / wt, 0, 90, CM256, waterfall=True)
+    ga = gray_from_image(a["image"], CM256, n, width)
+    gb = gray_from_image(b["image"], CM256, n, width, waterfall=True)
+    d = ga - gb
+    assert np.abs(d).max() <= 1 and (d != 0).sum() <= 2e-3 * d.size
+    assert np.abs(a["c_hist"].astype(np.int64) - b["c_hist"].astype(np.int64)).sum() <= 2 * (d != 0).sum()
+    assert np.abs(a["cB_hist"].astype(np.int64) - b["cB_hist"].astype(np.int64)).sum() <= 4e-3 * d.size
+    assert np.array_equal(a["gauge_amps"], b["gauge_amps"])
