@@ -59,6 +59,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float *fmin, const 
             atomicAdd(&cb_hist[CB_BINS - 1], 0ull - c);
         } else if (j == JH_BAD) {                    // d0 = +inf / NaN pixels were dropped: they belong to bin 0
             atomicAdd(&cb_hist[0], c);
+        } else if (j == JH_NAN) {                    // ~~(0.5 + NaN) == 0 (lib/worker.js:112)
+            atomicAdd(&c_hist[0], c);
         } else if (j < JH_BINS) {
             int bin, g;
             jh_decode(j, jc, cmap_len - 1, bin, g);

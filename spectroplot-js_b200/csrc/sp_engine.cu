@@ -509,6 +509,7 @@ static int prepare(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, boo
         p.jC = (float)(-color_norm * c1 / cmaxd);
         p.jD = (float)((cmaxd - (block_norm_db + rq->gain) * color_norm) / cmaxd);
     }
+    { static const char *dbg = getenv("SP_DEBUG_SKIP"); p.dbg = dbg ? atoi(dbg) : 0; }
     p.waterfall = rq->waterfall ? 1 : 0;
     p.channel_mode = rq->channel_mode ? 1 : 0;
     p.sub_r = j.plan.sub_r;

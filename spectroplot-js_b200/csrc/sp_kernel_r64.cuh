@@ -11,9 +11,11 @@
 //     log2|X|^2, so the joint index r + (cmax - g) determines the pair; it is formed by FFMA.SAT +
 //     FFMA on a 2^23 "magic" bias (no F2I, no integer clamps) and decoded once per render by
 //     finalize_kernel (jh_decode);
-//   * colour indices are staged as bytes in shared memory for a tile of 16 consecutive frames, so the
-//     transposed image store (lib/worker.js:117) writes 64 contiguous bytes per row from two lanes
-//     (half the L1 wavefronts of the 32-byte segments of the older kernels) and needs no registers;
+//   * colour indices are staged as bytes in shared memory (two halves of 8 consecutive frames), so the
+//     transposed image store (lib/worker.js:117) writes one full 32-byte sector per row and needs no
+//     registers; the LUT + store work of a finished half is done by a third warpgroup of four STORE
+//     warps (full / empty mbarriers, no CTA-wide barrier; register budget moved to the FFT warps with
+//     setmaxnreg), so it runs beside the FFT arithmetic instead of inside its instruction stream;
 //   * four independent frame streams per CTA (64 threads = 2 warps each, named barriers), one
 //     persistent CTA per SM; the raw bytes of a stream's next frame are prefetched by one TMA bulk
 //     copy INTO the stream's exchange buffer while the current frame is in registers.
@@ -27,7 +29,9 @@
 namespace sp {
 
 template <int FMT, bool SUB> struct R64Cfg {
-    static constexpr int N = 4096, T = 64, STREAMS = 4, THREADS = T * STREAMS, STEPS = 4, F = STREAMS * STEPS;   // 16 frames per tile
+    static constexpr int N = 4096, T = 64, STREAMS = 4, FFT_THREADS = T * STREAMS, STORE_THREADS = 128, THREADS = FFT_THREADS + STORE_THREADS;
+    static constexpr int STEPS = 4, F = STREAMS * STEPS;                         // 16 frames per tile
+    static constexpr int FFT_REGS = 232, STORE_REGS = 40;                        // 256 * 232 + 128 * 40 <= 65536
     static constexpr int SWB = SUB ? 8 : sample_width(FMT == FMT_RUNTIME ? CF64 : FMT);
     static constexpr bool OK = SUB || ((FMT != FMT_RUNTIME) && SWB <= 8);       // raw frame fits the exchange buffer
     static constexpr int XP = 66;                                                // exchange row pitch (float2): LDS.128 conflict-free
@@ -56,7 +60,7 @@ __device__ __forceinline__ void stream_barrier(int stream)
 
 // tw14: [64][14] float2 = W_4096^{t*k}, k = 1..7, 8, 16, 24, 32, 40, 48, 56
 template <int FMT, bool SUB>
-__global__ void __launch_bounds__(256, 1) render_r64_kernel(const Params p, const float2 *__restrict__ tw14,
+__global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, const float2 *__restrict__ tw14,
                                                             unsigned *__restrict__ tile_counter)
 {
     using B = R64Cfg<FMT, SUB>;
@@ -67,7 +71,7 @@ __global__ void __launch_bounds__(256, 1) render_r64_kernel(const Params p, cons
     // ((word >> shift) & 0x3fc) | lut_base: one SHF + one 3-input LOP3 per lookup
     const unsigned lut_base = (smem_u32(smem_r64) + 1023u) & ~1023u;
     unsigned char *s_x = smem_r64 + (lut_base - smem_u32(smem_r64)) + 1024;           // [4][X_BYTES] exchange / raw frame
-    unsigned *s_lut = reinterpret_cast<unsigned *>(s_x - 1024);                       // [256] RGBA, REVERSED (index cmax - g)
+    unsigned *s_lut = reinterpret_cast<unsigned *>(s_x - 1024);                       // [256] RGBA indexed by the staged byte (cmax - g, or g when range < 0)
     unsigned *s_stage = reinterpret_cast<unsigned *>(s_x + B::STREAMS * B::X_BYTES);  // [16][1026] colour bytes (4 bins per word)
     unsigned *s_jh = s_stage + F * B::ST_PITCH;                                       // [JH_SIZE] joint histogram
     float *s_win = reinterpret_cast<float *>(s_jh + JH_SIZE);                         // [64][64] (row t: window[64 a + t] at (a + 4t) mod 64)
@@ -75,7 +79,8 @@ __global__ void __launch_bounds__(256, 1) render_r64_kernel(const Params p, cons
     uint2 *s_mm = reinterpret_cast<uint2 *>(s_tw + T * B::TW_PITCH);                  // [16][2] per-warp min/max bit patterns of |X|^2
     uint64_t *s_mbar = reinterpret_cast<uint64_t *>(s_mm + F * 2);                    // [4]
     int *s_off = reinterpret_cast<int *>(s_mbar + B::STREAMS);                        // [4][2] misalignment of the staged frame
-    unsigned *s_tile = reinterpret_cast<unsigned *>(s_off + B::STREAMS * 2);          // [2] tile ring
+    uint64_t *s_full = reinterpret_cast<uint64_t *>(s_off + B::STREAMS * 2);          // [2] staging half h holds 8 finished frames
+    uint64_t *s_empty = s_full + 2;                                                   // [2] staging half h has been stored
 
     const int tid = threadIdx.x;
     const int s = tid >> 6;                 // stream
@@ -86,11 +91,11 @@ __global__ void __launch_bounds__(256, 1) render_r64_kernel(const Params p, cons
 
     for (int i = tid; i < JH_SIZE; i += B::THREADS) s_jh[i] = 0;
     const int cmax = p.cmap_len - 1;
-    for (int i = tid; i < 256; i += B::THREADS) s_lut[i] = i <= cmax ? p.lut[cmax - i] : 0u;
+    const JhConst jc = jh_const(p);
+    for (int i = tid; i < 256; i += B::THREADS) s_lut[i] = i <= cmax ? p.lut[jc.rev ? cmax - i : i] : 0u;
     for (int i = tid; i < T * B::TW_PITCH; i += B::THREADS) s_tw[i] = tw14[i];
     if constexpr (!SUB)
         for (int i = tid; i < N; i += B::THREADS) s_win[(i & 63) * B::WIN_PITCH + (((i >> 6) + 4 * (i & 63)) & 63)] = p.window[i];
-    const JhConst jc = jh_const(p);
     const unsigned jh_base = smem_u32(s_jh) - (JH_MAGIC_BITS << 2);      // address of joint bin j = S.bits * 4 + jh_base (mod 2^32)
     const int nfull = p.n_full, sub_r = p.sub_r;
 
@@ -115,28 +120,84 @@ __global__ void __launch_bounds__(256, 1) render_r64_kernel(const Params p, cons
     // tile -> first chunk-relative frame, sub-sequence
     auto tile_xr0 = [&](long long tile) -> long long { return (SUB ? tile / sub_r : tile) * F; };
 
+    (void)tile_counter;                     // tiles are dealt round-robin: every stream of the CTA walks the same list without a barrier
+    if (t == 0 && tid < B::FFT_THREADS) mbar_init(mbar, 1);
     if (tid == 0) {
-        s_tile[0] = atomicAdd(tile_counter, 1u);
-        s_tile[1] = atomicAdd(tile_counter, 1u);
+        for (int h = 0; h < 2; h++) { mbar_init(s_full + h, B::FFT_THREADS / 32); mbar_init(s_empty + h, B::STORE_THREADS / 32); }
     }
-    if (t == 0) {
-        mbar_init(mbar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    if (t == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    long long tile = s_tile[0], next_tile = s_tile[1];
-    int ring = 0;
+    long long tile = blockIdx.x;
+    unsigned kk = 0;                        // tiles done by this CTA (phase of the full / empty barriers)
+
+    if (tid >= B::FFT_THREADS) {
+        // ================= store warps: staged colour bytes -> LUT -> image rows (lib/worker.js:115-121) =================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B::STORE_REGS));
+        const int ht = tid - B::FFT_THREADS;
+        for (; tile < p.ntiles; tile += gridDim.x, kk++) {
+            const int k0sub = SUB ? (int)(tile % sub_r) : 0;
+            const long long xr0 = tile_xr0(tile);
+#pragma unroll 1
+            for (int h = 0; h < 2; h++) {
+                mbar_wait(s_full + h, kk & 1);
+                const size_t x0 = (size_t)(p.chunk_first + xr0) + 8 * h;
+#pragma unroll 1
+                for (int i = 0; i < 8; i++) {
+                    // bins k0 + 64*(4m + j), j = 0..3, of the half's 8 frames: one 32-byte sector per row
+                    const int id = ht + B::STORE_THREADS * i, k0 = id & 63, m = id >> 6;
+                    const unsigned *src = s_stage + (8 * h) * B::ST_PITCH + m * 64 + k0;
+                    unsigned w[8];
+#pragma unroll
+                    for (int f = 0; f < 8; f++) w[f] = src[f * B::ST_PITCH];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int kb = k0 + 64 * (4 * m + j);
+                        const int bin = SUB ? k0sub + sub_r * kb : kb;
+                        const int y = (nfull / 2 - bin) & (nfull - 1);                         // lib/worker.js:90
+                        uint32_t *rowp = reinterpret_cast<uint32_t *>(p.image) + (size_t)p.nframes * (size_t)y + x0;   // :117
+                        uint4 a, b;
+                        if (!(p.dbg & 4)) {
+                            a.x = lut_at(lut_base, w[0], j); a.y = lut_at(lut_base, w[1], j); a.z = lut_at(lut_base, w[2], j); a.w = lut_at(lut_base, w[3], j);
+                            b.x = lut_at(lut_base, w[4], j); b.y = lut_at(lut_base, w[5], j); b.z = lut_at(lut_base, w[6], j); b.w = lut_at(lut_base, w[7], j);
+                        } else { a = make_uint4(w[0], w[1], w[2], w[3]); b = make_uint4(w[4], w[5], w[6], w[7]); }
+                        if (!(p.dbg & 1)) st_global_256(rowp, a, b);
+                    }
+                }
+                if (ht < 8) {
+                    // per-frame min / max of the half's frames, folded across the two warps of their stream, as dB
+                    const int fl = 8 * h + ht;
+                    const long long xl = p.chunk_first + xr0 + fl;
+                    const uint2 m0 = s_mm[fl * 2], m1 = s_mm[fl * 2 + 1];
+                    const unsigned umn = min(m0.x, m1.x), umx = max(m0.y, m1.y);
+                    const float mn = fminf(0.0f, fmaf(fast_log2(__uint_as_float(umn)), p.c1, p.c0));       // lib/worker.js:82,102
+                    const float mx = fmaxf(-200.0f, fmaf(fast_log2(__uint_as_float(umx)), p.c1, p.c0));    // lib/worker.js:83,103
+                    if constexpr (SUB) {
+                        atomicMin(reinterpret_cast<unsigned *>(p.fmin) + xl, f2ord(mn));
+                        atomicMax(reinterpret_cast<unsigned *>(p.fmax) + xl, f2ord(mx));
+                    } else { p.fmin[xl] = mn; p.fmax[xl] = mx; }
+                }
+                __syncwarp();                                   // this warp is done reading the half (and s_mm)
+                if ((ht & 31) == 0) mbar_arrive(s_empty + h);
+            }
+        }
+    } else {
+    // ================= FFT warps: four frame streams =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(B::FFT_REGS));
     unsigned fpar = 0;                      // parity of this stream's frame counter (mbarrier phase, s_off slot)
     if (t == 0 && tile < p.ntiles) stage(tile_xr0(tile) + s, SUB ? (int)(tile % sub_r) : 0, 0);
 
     while (tile < p.ntiles) {
         const int k0sub = SUB ? (int)(tile % sub_r) : 0;
         const long long xr0 = tile_xr0(tile);
-        if (tid == 0) s_tile[ring] = atomicAdd(tile_counter, 1u);       // the tile after next (read after the tile barrier)
+        const long long next_tile = tile + gridDim.x;
 
 #pragma unroll 1
         for (int step = 0; step < B::STEPS; step++) {
             const int fl = step * B::STREAMS + s;                       // frame of the tile handled by this stream now
+            int half = step >> 1;                                       // staging half of this frame
+            // (opaque to the optimiser: with `step & 1` known, nvcc 12.9 folded 8*(step >> 1) into 4*step and
+            // produced a misaligned mbarrier address)
+            asm volatile("" : "+r"(half));
             cf v[64];
             // ---------------- load + decode + window (lib/worker.js:70-75) ----------------
             mbar_wait(mbar, fpar);
@@ -201,6 +262,8 @@ __global__ void __launch_bounds__(256, 1) render_r64_kernel(const Params p, cons
                 if (step < B::STEPS - 1) stage(xr0 + fl + B::STREAMS, k0sub, fpar);
                 else if (next_tile < p.ntiles) stage(tile_xr0(next_tile) + s, SUB ? (int)(next_tile % sub_r) : 0, fpar);
             }
+            // first frame of this stream in staging half step/2: the store warps must be done with the half (previous tile)
+            if ((step & 1) == 0) mbar_wait(s_empty + half, (kk + 1) & 1);
             dft<64>(v);                                                 // v[k1] is bin t + 64*k1
 
             // ---------------- per-bin epilogue (lib/worker.js:85-122) ----------------
@@ -244,7 +307,7 @@ __global__ void __launch_bounds__(256, 1) render_r64_kernel(const Params p, cons
                 // rare (warp-uniform): the frame holds |X|^2 == 0 (flushed: d0 = -inf), +inf or NaN.  Count them for
                 // the bin-0 fix-ups (lib/worker.js:105-106: ~~(+-Infinity) == ~~NaN == 0) and redo min / max the way
                 // the reference's `<` / `>` see them (NaN never wins).
-                unsigned nzero = 0, nbad = 0;
+                unsigned nzero = 0, nbad = 0, nnan = 0;
                 float mn = __int_as_float(0x7f800000), mx = 0.0f;
 #pragma unroll
                 for (int i = 0; i < 64; i++) {
@@ -252,65 +315,36 @@ __global__ void __launch_bounds__(256, 1) render_r64_kernel(const Params p, cons
                     const float abs2 = fmaf(vi.x, vi.x, vi.y * vi.y);
                     nzero += abs2 < 1.17549435e-38f ? 1u : 0u;
                     nbad += !(abs2 <= 3.402823466e38f) ? 1u : 0u;
+                    nnan += abs2 != abs2 ? 1u : 0u;
                     mn = fminf(mn, abs2 < 1.17549435e-38f ? 0.0f : abs2);
                     mx = fmaxf(mx, abs2);
                 }
                 nzero = __reduce_add_sync(0xffffffffu, nzero);
                 nbad = __reduce_add_sync(0xffffffffu, nbad);
+                nnan = __reduce_add_sync(0xffffffffu, nnan);
                 umn = __reduce_min_sync(0xffffffffu, __float_as_uint(mn));
                 umx = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
                 if ((t & 31) == 0) {
                     if (nzero) atomicAdd(&s_jh[JH_ZERO], nzero);
                     if (nbad) atomicAdd(&s_jh[JH_BAD], nbad);
+                    if (nnan) {                 // NaN pixels were counted under the joint index sat(NaN) = 0 yields: move them
+                        float Yn;
+                        const float Sn = jh_eval(__int_as_float(0x7fffffff), jc, Yn);
+                        atomicSub(&s_jh[__float_as_uint(Sn) - JH_MAGIC_BITS], nnan);
+                        atomicAdd(&s_jh[JH_NAN], nnan);
+                    }
                 }
             }
             if ((t & 31) == 0) s_mm[fl * 2 + (t >> 5)] = make_uint2(umn, umx);
+            if (step & 1) {                 // this warp has staged its last frame of half step/2 (and its s_mm entries)
+                __syncwarp();
+                if ((t & 31) == 0) mbar_arrive(s_full + half);
+            }
         } // steps
-
-        __syncthreads();                    // the tile's 16 frames are staged; s_mm and s_tile[ring] are written
-
-        // ---------------- row stores: 2 lanes x 8 frames x RGBA = 64 contiguous bytes per bin (lib/worker.js:117) ----------------
-        {
-            const size_t x0 = (size_t)(p.chunk_first + xr0);
-#pragma unroll 1
-            for (int it = 0; it < 8; it++) {
-                const int id = tid + B::THREADS * it;
-                const int half = id & 1, q = id >> 1, k0 = q & 63, m = q >> 6;
-                const unsigned *src = s_stage + (8 * half) * B::ST_PITCH + m * 64 + k0;
-                unsigned w[8];
-#pragma unroll
-                for (int i = 0; i < 8; i++) w[i] = src[i * B::ST_PITCH];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int kk = k0 + 64 * (4 * m + j);
-                    const int bin = SUB ? k0sub + sub_r * kk : kk;
-                    const int y = (nfull / 2 - bin) & (nfull - 1);                             // lib/worker.js:90
-                    uint32_t *rowp = reinterpret_cast<uint32_t *>(p.image) + (size_t)p.nframes * (size_t)y + x0 + 8 * half;
-                    uint4 a, b;
-                    a.x = lut_at(lut_base, w[0], j); a.y = lut_at(lut_base, w[1], j); a.z = lut_at(lut_base, w[2], j); a.w = lut_at(lut_base, w[3], j);
-                    b.x = lut_at(lut_base, w[4], j); b.y = lut_at(lut_base, w[5], j); b.z = lut_at(lut_base, w[6], j); b.w = lut_at(lut_base, w[7], j);
-                    st_global_256(rowp, a, b);
-                }
-            }
-            // per-frame min / max of the tile, folded across the stream's two warps and converted to dB
-            if (tid < F) {
-                const long long xl = p.chunk_first + xr0 + tid;
-                const uint2 m0 = s_mm[tid * 2], m1 = s_mm[tid * 2 + 1];
-                const unsigned umn = min(m0.x, m1.x), umx = max(m0.y, m1.y);
-                const float mn = fminf(0.0f, fmaf(fast_log2(__uint_as_float(umn)), p.c1, p.c0));       // lib/worker.js:82,102
-                const float mx = fmaxf(-200.0f, fmaf(fast_log2(__uint_as_float(umx)), p.c1, p.c0));    // lib/worker.js:83,103
-                if constexpr (SUB) {
-                    atomicMin(reinterpret_cast<unsigned *>(p.fmin) + xl, f2ord(mn));
-                    atomicMax(reinterpret_cast<unsigned *>(p.fmax) + xl, f2ord(mx));
-                } else { p.fmin[xl] = mn; p.fmax[xl] = mx; }
-            }
-        }
-        const unsigned fetched = s_tile[ring];
-        __syncthreads();                    // staging, s_mm and the tile ring may be rewritten
         tile = next_tile;
-        next_tile = fetched;
-        ring ^= 1;
+        kk++;
     } // tiles
+    } // FFT warps
 
     __syncthreads();
     for (int i = tid; i < JH_SIZE; i += B::THREADS)

@@ -55,6 +55,7 @@ struct Params {
     // joint (dB bin, colour index) histogram of render_r64_kernel (decoded by finalize_kernel)
     unsigned long long *j_hist;    // [JH_SIZE]
     float jA, jB, jC, jD;          // see jh_eval()
+    int dbg;                       // SP_DEBUG_SKIP bit mask (performance experiments only): 1 image stores, 4 LUT lookups (store warps of render_r64_kernel)
 };
 
 template <int LOG2N> struct Cfg {
@@ -101,7 +102,7 @@ __host__ __device__ inline size_t main_smem_bytes(int smem_x_float2, int cmap_le
 // Joint histogram (render_r64_kernel).  Per pixel, with l2 = log2|X|^2 and d0 = c1*l2 + c0 (= dBfs - gain):
 //   r  = RN(sat(jA*l2 + jB) * RCAP),  jA*l2 + jB = (2.0 - 10*d0) / RCAP   : RN(x - 0.5) == trunc(x) for the
 //        x = 2.5 - 10*d0 of the table above (off quantisation ties), saturating at 0 and RCAP = 1003
-//   g' = RN(sat(jC*l2 + jD) * cmax) subtracted from cmax, jC*l2 + jD = (cmax - (d0 + gain)*color_norm) / cmax
+//   g' = RN(sat(jC*l2 + jD) * cmax) subtracted from cmax (as is when range < 0), jC*l2 + jD = (cmax - (d0 + gain)*color_norm) / cmax
 //        (lib/worker.js:111-112: the colour index g = cmax - g', clamped by the saturation)
 // Both roundings are done by adding 2^23 inside an FFMA, so S = 2^23 + r + g' and Y = 2^23 + g' come out of
 // four FMA-pipe instructions with no F2I and no integer clamp.  r falls and g rises with l2, so j = r + g'
@@ -110,20 +111,25 @@ __host__ __device__ inline size_t main_smem_bytes(int smem_x_float2, int cmap_le
 // +inf, NaN) take the ordinary path and are corrected per frame through two extra counters:
 //   JH_ZERO  pixels with d0 = -inf: counted as r = RCAP (bin 999) -> move them to bin 0  (~~(+Infinity) == 0)
 //   JH_BAD   pixels with d0 = +inf or NaN: counted as r = 0 (dropped) -> add them to bin 0
+//   JH_NAN   NaN pixels: sat(NaN) = 0 gives them the joint index of some ordinary level; the kernel takes them out of that
+//            counter again and counts them here -> colour index 0 (the dB bin comes from JH_BAD)
 // ---------------------------------------------------------------------------------------------
 constexpr int JH_RCAP = 1003;
 constexpr int JH_BINS = JH_RCAP + 1 + 256;
-constexpr int JH_ZERO = JH_BINS, JH_BAD = JH_BINS + 1, JH_SIZE = JH_BINS + 4;
+constexpr int JH_ZERO = JH_BINS, JH_BAD = JH_BINS + 1, JH_NAN = JH_BINS + 2, JH_SIZE = JH_BINS + 4;
 constexpr unsigned JH_MAGIC_BITS = 0x4B000000u;       // 2^23
 
-struct JhConst { float A, B, C, D, rcap, ncmax, ymagic; };
+struct JhConst { float A, B, C, D, rcap, ncmax, ymagic; int rev; };
 __host__ __device__ __forceinline__ JhConst jh_const(const Params &p)
 {
     JhConst c;
     c.A = p.jA; c.B = p.jB; c.C = p.jC; c.D = p.jD;
     c.rcap = (float)JH_RCAP;
-    c.ncmax = -(float)(p.cmap_len - 1);
-    c.ymagic = (float)(p.cmap_len - 1) + 8388608.0f;
+    // the second term must fall with l2 like r does: cmax - g when the colour index rises with the level (range > 0),
+    // g itself when it falls (range < 0)
+    c.rev = p.jC >= 0.0f;
+    c.ncmax = c.rev ? -(float)(p.cmap_len - 1) : (float)(p.cmap_len - 1);
+    c.ymagic = (c.rev ? (float)(p.cmap_len - 1) : 0.0f) + 8388608.0f;
     return c;
 }
 // returns S = 2^23 + r + g'; Y = 2^23 + g'
@@ -172,7 +178,7 @@ __device__ inline bool jh_decode(int j, const JhConst &c, int cmax, int &bin, in
     const int J = (int)(__float_as_uint(jh_eval(ord2f(lo), c, Y)) - JH_MAGIC_BITS);
     const int gp = (int)(__float_as_uint(Y) - JH_MAGIC_BITS);
     const int r = J - gp;
-    g = cmax - gp;
+    g = c.rev ? cmax - gp : gp;
     bin = r == 0 ? -1 : (r <= 2 ? 0 : (r <= 1001 ? r - 2 : CB_BINS - 1));
     return J == j;
 }
