@@ -289,10 +289,11 @@ def run_ours(args):
         kms = float(np.mean(kern_ms)) if len(kern_ms) else ms_step
         alg_bytes = ALG_BYTES_PER_SAMPLE * sh["sample_count"]
         achieved = alg_bytes / (kms * 1e-3) / 1e9
-        traffic = None
+        traffic, kname = None, "render kernel of " + eng.kernel_plan(FMT, N_FFT)
         try:
             with open(os.path.join(ROOT, "profiles", "latest_traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                lt = json.load(f)
+                traffic, kname = lt.get("dram_bytes_per_launch"), lt.get("kernel", kname)
         except Exception:
             pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -304,7 +305,7 @@ def run_ours(args):
                            "l2": "inputs (419 MB) and outputs (419 MB) per GPU exceed the 126 MB L2; no flush needed",
                            "kernel_plan": eng.kernel_plan(FMT, N_FFT)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "peak_source": how, "kernel": "render_fast_kernel<CS16> (N=4096 fast path)",
+                             "traffic": traffic, "peak_source": how, "kernel": kname,
                              "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms, "steps": e2e_steps},

@@ -386,7 +386,7 @@ def test_r64_non_finite_pixels(engine):
     assert int(np.abs(gpu["cB_hist"].astype(np.int64) - ora.cB_hist.astype(np.int64)).sum()) <= ties
     assert int(np.abs(gpu["c_hist"].astype(np.int64) - ora.c_hist.astype(np.int64)).sum()) <= ties
     assert gpu["cB_hist"][0] == ora.cB_hist[0] and gpu["c_hist"][0] >= 2 * n
-    assert gpu["dBfs_min"] == ora.dBfs_min and gpu["dBfs_max"] == ora.dBfs_max
+    assert gpu["dBfs_min"] == ora.dBfs_min == -np.inf and abs(gpu["dBfs_max"] - ora.dBfs_max) <= DB_TOL
     # +inf samples and |X|^2 beyond fp32 range are outside the reference's domain (samples lie in [-1, 1]); which bins
     # become NaN and which +inf then depends on the butterfly order, so only the bookkeeping is checked: every pixel is
     # counted once in c_hist, and the other frames are untouched
