@@ -199,8 +199,8 @@ def run_ours(args):
     eng.synth_fill(d_in.data_ptr(), FMT, sh["sample_first"], sh["sample_count"], total_samples, SEED)
     d_img = torch.empty(4 * width * N_FFT, dtype=torch.uint8, device=dev)
     d_g = torch.empty(3 * width, dtype=torch.uint8, device=dev)
-    d_hist = torch.zeros(1000 + len(cm), dtype=torch.int64, device=dev)   # cB_hist | c_hist (u64 counters)
-    d_mm = torch.zeros(2, dtype=torch.float64, device=dev)
+    # cB_hist | c_hist (u64 counters) | dBfs_min, dBfs_max: one buffer, so the multi-GPU merge is ONE all-gather
+    d_stats, d_hist, d_mm, d_gath = sharding.stats_buffers(torch, 1000 + len(cm), world, dev)
     shard = sharding.shard_fields(sh, total_samples, SW, total_width) if world > 1 else None
 
     def step():
@@ -208,8 +208,8 @@ def run_ours(args):
                                     byte_length=nbytes_in, shard=shard)
         rp = eng.render_enqueue(rq, d_img.data_ptr(), (d_g.data_ptr(), d_g.data_ptr() + width, d_g.data_ptr() + 2 * width),
                                 d_hist.data_ptr(), d_hist.data_ptr() + 8000, d_mm.data_ptr())
-        if world > 1:                                       # merge: histograms add, min/max fold
-            sharding.allreduce_stats(dist, d_hist, d_mm)
+        if world > 1:                                       # the exchange step: one ~10 KB all-gather over NVLink
+            sharding.gather_stats(dist, d_stats, d_gath)
         return rp
 
     def barrier():
@@ -254,7 +254,11 @@ def run_ours(args):
     value = total_samples / (ms_step * 1e-3) / 1e6
 
     # sanity of the timed output: histogram totals (size-independent property)
-    c_total = int(d_hist[1000:].sum().item())
+    if world > 1:                                           # histograms add, min/max fold (lib/spectroplot.js:1229-1238)
+        m_hist, m_min, m_max = sharding.fold_gathered(torch, d_gath, 1000 + len(cm))
+    else:
+        m_hist = d_hist
+    c_total = int(m_hist[1000:].sum().item())
     assert c_total == total_width * N_FFT, (c_total, total_width * N_FFT)
 
     # ---- end to end through the host-buffer API (pinned host memory both ways)
@@ -310,7 +314,8 @@ def run_ours(args):
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms, "steps": e2e_steps},
                 "gpu_launches": int(launches), "clocks": clocks,
-                "parity_check": {"c_hist_total": c_total, "dBfs_min": rp.dBfs_min, "dBfs_max": rp.dBfs_max}}
+                "parity_check": {"c_hist_total": c_total, "dBfs_min": m_min if world > 1 else rp.dBfs_min,
+                                 "dBfs_max": m_max if world > 1 else rp.dBfs_max}}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(line), flush=True)

@@ -793,7 +793,7 @@ static int finish(sp_engine *e, sp_reply *rp);
 static long long pipeline_chunk_frames(const sp_request *rq)
 {
     const char *env = getenv("SP_PIPE_MB");                  // chunk size in MB; 0 disables the pipeline
-    const long long mb = env ? atoll(env) : 32;
+    const long long mb = env ? atoll(env) : 16;     // 16 MB: best of 8..128 on B200 + PCIe 5 (profiles/r01_e2e_chunk_sweep.txt)
     if (mb <= 0) return 0;
     const double in_per_frame = (double)rq->byte_length / (double)rq->width;
     const double out_per_frame = 4.0 * rq->n;

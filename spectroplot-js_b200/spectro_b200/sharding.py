@@ -54,3 +54,26 @@ def allreduce_stats(dist, hist, minmax):
     dist.all_reduce(minmax, op=dist.ReduceOp.MIN)      # min(min) and -max(max) in one MIN reduction
     minmax[1].neg_()
     return hist, minmax
+
+
+def stats_buffers(torch, hist_len: int, world: int, device):
+    """Buffers of the one-collective merge: `local` = [cB_hist | c_hist | dBfs_min, dBfs_max as float64 bits] (int64),
+    written by the engine (histogram pointer = local, min/max pointer = local[hist_len:]), and `gathered` =
+    [world][hist_len + 2], filled by gather_stats().  -> (local, hist_view, minmax_view_f64, gathered)"""
+    local = torch.zeros(hist_len + 2, dtype=torch.int64, device=device)
+    gathered = torch.zeros(world, hist_len + 2, dtype=torch.int64, device=device)
+    return local, local[:hist_len], local[hist_len:].view(torch.float64), gathered
+
+
+def gather_stats(dist, local, gathered):
+    """The one exchange step of the multi-GPU path as ONE collective: every rank's histograms and min/max
+    (about 10 KB) are all-gathered; fold_gathered() finishes the merge where the reply is read."""
+    dist.all_gather_into_tensor(gathered.view(-1), local)
+    return gathered
+
+
+def fold_gathered(torch, gathered, hist_len: int):
+    """-> (hist int64 [hist_len] summed over ranks, dBfs_min, dBfs_max) like lib/spectroplot.js:1229-1238."""
+    hist = gathered[:, :hist_len].sum(0)
+    mm = gathered[:, hist_len:].contiguous().view(torch.float64)
+    return hist, min(0.0, float(mm[:, 0].min())), max(-200.0, float(mm[:, 1].max()))

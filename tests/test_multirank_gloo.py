@@ -49,7 +49,13 @@ def _worker(rank, world, port, q):
     img, cB, c, mn, mx = _render_shard_with_oracle(O, shard_buf, sh, stride, w, wt, cm)
     hist = torch.from_numpy(np.concatenate([cB, c]))
     mm = torch.tensor([mn, mx], dtype=torch.float64)
+    # the one-collective variant used by bench.py (all-gather + fold) must agree with the two all-reduces
+    local, hview, mmview, gathered = sharding.stats_buffers(torch, len(hist), world, "cpu")
+    hview.copy_(hist); mmview.copy_(mm)
+    sharding.gather_stats(dist, local, gathered)
+    g_hist, g_min, g_max = sharding.fold_gathered(torch, gathered, len(hist))
     sharding.allreduce_stats(dist, hist, mm)
+    assert torch.equal(g_hist, hist) and g_min == float(mm[0]) and g_max == float(mm[1])
     tiles = [None] * world
     dist.all_gather_object(tiles, (sh["frame_first"], img))
     if rank == 0:
