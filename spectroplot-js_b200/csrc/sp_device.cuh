@@ -186,14 +186,13 @@ __device__ __forceinline__ float2 decode_raw(const uint8_t *__restrict__ buf, lo
         int b0 = p[0], b1 = p[1], b2 = p[2];
         return make_float2((float)sext(((b1 & 15) << 8) | b0, 12), (float)sext((b2 << 4) | (b1 >> 4), 12));
     } else if constexpr (FMT == CS16) {
-        // two I2F.S16 reading the low / high half of the loaded word directly (no shift)
-        unsigned v = *reinterpret_cast<const unsigned *>(buf + 4 * s);
-        short lo, hi;
-        float2 r;
-        asm("mov.b32 {%0, %1}, %2;" : "=h"(lo), "=h"(hi) : "r"(v));
-        asm("cvt.rn.f32.s16 %0, %1;" : "=f"(r.x) : "h"(lo));
-        asm("cvt.rn.f32.s16 %0, %1;" : "=f"(r.y) : "h"(hi));
-        return r;
+        // int16 -> fp32 without the conversion unit (I2F sits behind the same MIO queue as the shared-memory
+        // traffic of the fused kernels): bias both halves to unsigned (one LOP3), drop each into the mantissa of
+        // 2^23 (one PRMT each: 0x4B00xxxx = 8388608 + x) and subtract 2^23 + 2^15; every step is exact.
+        const unsigned v = *reinterpret_cast<const unsigned *>(buf + 4 * s) ^ 0x80008000u;
+        const float lo = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7610));
+        const float hi = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7632));
+        return make_float2(__fadd_rn(lo, -8421376.0f), __fadd_rn(hi, -8421376.0f));
     } else if constexpr (FMT == CU16) {
         unsigned v = *reinterpret_cast<const unsigned *>(buf + 4 * s);
         return make_float2((float)(2 * (int)(v & 0xffff) - 65535), (float)(2 * (int)(v >> 16) - 65535));

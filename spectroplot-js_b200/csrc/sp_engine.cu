@@ -699,11 +699,14 @@ static int enqueue_frames(sp_engine *e, Job &j, Params &p)
         const float2 *tw_full = nullptr;
         int rc = get_twiddles(e, n, &tw_full);
         if (rc) return rc;
-        // chunk = one full wave of the sub-frame kernel: 2 slots x sm_count tiles of 8 sub-frames (77.6 MB of
-        // scratch on 148 SMs, L2 resident); SP_SCRATCH_MB overrides
-        long long ch = (long long)8 * 2 * e->sm_count / R;
+        // frames per chunk: a 1 GB scratch by default.  An L2-sized scratch (<= 96 MB) keeps the 16 B/sample of scratch
+        // traffic out of HBM but leaves each launch with about one wave of tiles; measured on B200 the large chunk wins
+        // (C5: 2.10 -> 1.56 ms, C3 x1: 1.28 -> 0.70 ms, profiles/r01_fourstep_scratch_sweep.txt).  SP_SCRATCH_MB overrides.
+        long long ch = (long long)(((size_t)1024 << 20) / ((size_t)n * 8));
         if (const char *s = getenv("SP_SCRATCH_MB"))
             if (atoi(s) > 0) ch = (long long)(((size_t)atoi(s) << 20) / ((size_t)n * 8));
+        ch = ch / 16 * 16;
+        if (ch < 16) ch = 16;
         ch = ch / 8 * 8;
         if (ch < 8) ch = 8;
         if (ch > p.nframes) ch = (p.nframes + 7) / 8 * 8;
