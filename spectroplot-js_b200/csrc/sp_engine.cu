@@ -25,7 +25,8 @@ using sp::Params;
     extern "C" cudaError_t sp_rl_##tag(int, const Params *, int, size_t, cudaStream_t, int *) __attribute__((weak)); \
     extern "C" cudaError_t sp_pl_##tag(int, const Params *, float2 *, const float2 *, cudaStream_t) __attribute__((weak)); \
     extern "C" cudaError_t sp_fl_##tag(int, const Params *, int, cudaStream_t, unsigned *, const float2 *, const float2 *, int *) __attribute__((weak)); \
-    extern "C" cudaError_t sp_r64_##tag(int, const Params *, int, cudaStream_t, unsigned *, const float2 *, int *) __attribute__((weak));
+    extern "C" cudaError_t sp_r64_##tag(int, const Params *, int, cudaStream_t, unsigned *, const float2 *, int *) __attribute__((weak)); \
+    extern "C" cudaError_t sp_rc_##tag(int, const Params *, int, cudaStream_t, const float2 *, int *) __attribute__((weak));
 SP_DECL(rt) SP_DECL(cu4) SP_DECL(cs4) SP_DECL(cu8) SP_DECL(cs8) SP_DECL(cu12) SP_DECL(cs12) SP_DECL(cu16)
 SP_DECL(cs16) SP_DECL(cu32) SP_DECL(cs32) SP_DECL(cu64) SP_DECL(cs64) SP_DECL(cf32) SP_DECL(cf64)
 
@@ -33,6 +34,7 @@ typedef cudaError_t (*render_fn)(int, const Params *, int, size_t, cudaStream_t,
 typedef cudaError_t (*prepass_fn)(int, const Params *, float2 *, const float2 *, cudaStream_t);
 typedef cudaError_t (*fast_fn)(int, const Params *, int, cudaStream_t, unsigned *, const float2 *, const float2 *, int *);
 typedef cudaError_t (*r64_fn)(int, const Params *, int, cudaStream_t, unsigned *, const float2 *, int *);
+typedef cudaError_t (*rc_fn)(int, const Params *, int, cudaStream_t, const float2 *, int *);
 
 static render_fn render_for(int fmt)
 {
@@ -57,6 +59,12 @@ static r64_fn r64_for(int fmt)
     static const r64_fn tab[SP_FORMAT_COUNT] = { sp_r64_cu4, sp_r64_cs4, sp_r64_cu8, sp_r64_cs8, sp_r64_cu12, sp_r64_cs12,
         sp_r64_cu16, sp_r64_cs16, sp_r64_cu32, sp_r64_cs32, sp_r64_cu64, sp_r64_cs64, sp_r64_cf32, sp_r64_cf64 };
     return tab[fmt];                                    // specialised formats only (the runtime-switch build has no raw staging)
+}
+static rc_fn rc_for(int fmt)
+{
+    static const rc_fn tab[SP_FORMAT_COUNT] = { sp_rc_cu4, sp_rc_cs4, sp_rc_cu8, sp_rc_cs8, sp_rc_cu12, sp_rc_cs12,
+        sp_rc_cu16, sp_rc_cs16, sp_rc_cu32, sp_rc_cs32, sp_rc_cu64, sp_rc_cs64, sp_rc_cf32, sp_rc_cf64 };
+    return tab[fmt];
 }
 static bool specialised(int fmt)
 {
@@ -309,6 +317,18 @@ static bool use_r64()
     static const char *v = getenv("SP_FAST");
     return !(v && !strcmp(v, "dbx"));
 }
+// 64 x C path table (N = 512, 1024, 2048): tw14 [C][14] = W_N^{t*k}, k = 1..7, 8, 16, .., 56
+static int get_rc_table(sp_engine *e, int n, const float2 **tw14)
+{
+    static const int ks[14] = { 1, 2, 3, 4, 5, 6, 7, 8, 16, 24, 32, 40, 48, 56 };
+    auto it = e->twA.find(-100000 - n);
+    if (it != e->twA.end()) { *tw14 = it->second; return SP_OK; }
+    const int c = n / 64;
+    std::vector<float2> h((size_t)c * 14);
+    for (int t = 0; t < c; t++) for (int i = 0; i < 14; i++) h[(size_t)t * 14 + i] = twid((long long)t * ks[i], n);
+    return upload_table(e, e->twA, -100000 - n, h, tw14);
+}
+
 struct Plan {
     int log2k = 0;       // kernel FFT size (log2)
     int sub_r = 1;       // pre-pass radix (n = sub_r * 4096 when > 1)
@@ -345,6 +365,11 @@ extern "C" const char *sp_kernel_plan(sp_engine *e, int format, int n, int chann
     snprintf(buf, sizeof buf, "%s%srender_kernel<N=%d,%s> tile=%d frames smem_x=%d B%s", pl.sub_r > 1 ? "prepass_kernel<R=" : "",
              pl.sub_r > 1 ? (std::to_string(pl.sub_r) + "> + ").c_str() : "", 1 << pl.log2k,
              specialised(format) ? k_names[format] : "runtime-format", pl.tile, pl.smem_x * 8, channel_mode ? " +splitreal" : "");
+    if (pl.log2k >= 9 && pl.log2k <= 11 && !channel_mode && !getenv("SP_NO_FAST") && use_r64() && rc_for(format) && sp::sample_width(format) <= 8) {
+        const size_t l = strlen(buf);
+        snprintf(buf + l, sizeof buf - l, " | spectrogram fast path: render_rc_kernel<N=64x%d, tile=%d frames> (one exchange, joint histogram, TMA-staged input)",
+                 (1 << pl.log2k) / 64, 65536 >> pl.log2k);
+    }
     if (pl.log2k == 12 && !channel_mode && !getenv("SP_NO_FAST")) {
         const size_t l = strlen(buf);
         if (use_r64() && (pl.sub_r > 1 ? sp_r64_cf32 != nullptr : r64_for(format) != nullptr) && (pl.sub_r > 1 || sp::sample_width(format) <= 8))
@@ -639,6 +664,37 @@ static int launch_r64_kernel(sp_engine *e, r64_fn fn, Params &q, long long *nfas
     return SP_OK;
 }
 
+// Frames [0, *nfast) of the chunk go through render_rc_kernel (N = 512 / 1024 / 2048): whole tiles of 65536 / N frames inside the buffer.
+static int launch_rc_kernel(sp_engine *e, rc_fn fn, int log2n, Params &q, long long *nfast)
+{
+    const int n = 1 << log2n, tile = 65536 / n;
+    long long nf = q.chunk_frames / tile * tile;
+    const long long sw = sp::sample_width(q.format);
+    auto inside = [&](long long xr) {
+        const long long xgl = q.frame_first + q.chunk_first + xr;
+        const long long p0 = (long long)(0.5 + q.stride * (double)xgl) - q.sample_base;       // lib/worker.js:72
+        return p0 >= 0 && (unsigned long long)(p0 + n) * (unsigned long long)sw <= q.valid_bytes;
+    };
+    while (nf > 0 && !inside(nf - 1)) nf -= tile;
+    if (nf > 0 && !inside(0)) nf = 0;
+    *nfast = nf;
+    if (nf == 0) return SP_OK;
+    const float2 *tw14 = nullptr;
+    int rc = get_rc_table(e, n, &tw14), occ = 0;
+    if (rc) return rc;
+    CU(fn(log2n, &q, 0, e->stream, tw14, &occ));
+    if (occ < 1) { *nfast = 0; return SP_OK; }
+    Params r = q;
+    r.chunk_frames = nf;
+    r.ntiles = nf / tile;
+    const int grid = (int)(r.ntiles < e->sm_count ? r.ntiles : e->sm_count);
+    prof_begin(e);
+    CU(fn(log2n, &r, grid, e->stream, tw14, nullptr));
+    prof_end(e);
+    e->launches++;
+    return SP_OK;
+}
+
 // Enqueue all kernels of a job on e->stream (bracketed by the timing events).
 static int enqueue_begin(sp_engine *e, Job &j)
 {
@@ -664,6 +720,13 @@ static int enqueue_frames(sp_engine *e, Job &j, Params &p)
         if (j.plan.log2k == 12 && fast_eligible(p) && use_r64() && r64_for(fmt) && (q.chunk_first % 16 == 0)) {
             long long nfast = 0;
             int rc = launch_r64_kernel(e, r64_for(fmt), q, &nfast);
+            if (rc) return rc;
+            q.chunk_first += nfast;
+            q.chunk_frames -= nfast;
+        }
+        if (j.plan.log2k >= 9 && j.plan.log2k <= 11 && fast_eligible(p) && use_r64() && rc_for(fmt) && (q.chunk_first % 8 == 0)) {
+            long long nfast = 0;
+            int rc = launch_rc_kernel(e, rc_for(fmt), j.plan.log2k, q, &nfast);
             if (rc) return rc;
             q.chunk_first += nfast;
             q.chunk_frames -= nfast;

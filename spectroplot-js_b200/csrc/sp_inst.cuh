@@ -6,6 +6,7 @@
 #include "sp_kernels.cuh"
 #include "sp_kernel_fast.cuh"
 #include "sp_kernel_r64.cuh"
+#include "sp_kernel_rc.cuh"
 
 namespace sp {
 
@@ -112,6 +113,33 @@ static cudaError_t launch_r64_v(const Params &p, int grid, cudaStream_t st, unsi
     }
 }
 
+// N = 512 / 1024 / 2048 as 64 x C (sp_kernel_rc.cuh): same CTA shape as the 64 x 64 kernel.
+template <int LOG2C, int FMT>
+static cudaError_t launch_rc_v(const Params &p, int grid, cudaStream_t st, const float2 *tw14, int *occ_out)
+{
+    using B = RcCfg<LOG2C, FMT>;
+    if constexpr (!B::OK) {
+        if (occ_out) *occ_out = 0;
+        return occ_out ? cudaSuccess : cudaErrorInvalidValue;
+    } else {
+        auto kfn = render_rc_kernel<LOG2C, FMT>;
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+            attr_done = true;
+        }
+        if (occ_out) {
+            int nb = 0;
+            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, B::THREADS, B::SMEM_BYTES);
+            *occ_out = nb;
+            return e;
+        }
+        kfn<<<grid, B::THREADS, B::SMEM_BYTES, st>>>(p, tw14);
+        return cudaGetLastError();
+    }
+}
+
 } // namespace sp
 
 #define SP_CAT2(a, b) a##b
@@ -139,6 +167,15 @@ extern "C" cudaError_t SP_CAT(sp_r64_, SP_INST_TAG)(int sub, const sp::Params *p
         if (sub) return sp::launch_r64_v<SP_INST_FMT, true>(*p, grid, st, tile_counter, tw14, occ_out);
     } else if (sub) return cudaErrorInvalidValue;
     return sp::launch_r64_v<SP_INST_FMT, false>(*p, grid, st, tile_counter, tw14, occ_out);
+}
+extern "C" cudaError_t SP_CAT(sp_rc_, SP_INST_TAG)(int log2n, const sp::Params *p, int grid, cudaStream_t st, const float2 *tw14, int *occ_out)
+{
+    switch (log2n) {
+    case 9: return sp::launch_rc_v<3, SP_INST_FMT>(*p, grid, st, tw14, occ_out);
+    case 10: return sp::launch_rc_v<4, SP_INST_FMT>(*p, grid, st, tw14, occ_out);
+    case 11: return sp::launch_rc_v<5, SP_INST_FMT>(*p, grid, st, tw14, occ_out);
+    default: return cudaErrorInvalidValue;
+    }
 }
 extern "C" cudaError_t SP_CAT(sp_pl_, SP_INST_TAG)(int r, const sp::Params *p, float2 *out, const float2 *tw_full,
                                                     cudaStream_t st)

@@ -422,3 +422,38 @@ def test_r64_matches_generic_kernel(engine):
     assert np.abs(a["c_hist"].astype(np.int64) - b["c_hist"].astype(np.int64)).sum() <= 2 * (d != 0).sum()
     assert np.abs(a["cB_hist"].astype(np.int64) - b["cB_hist"].astype(np.int64)).sum() <= 4e-3 * d.size
     assert np.array_equal(a["gauge_amps"], b["gauge_amps"])
+
+
+# ------------------------------------------------------------------ N = 512 / 1024 / 2048 as 64 x C (render_rc_kernel)
+@pytest.mark.parametrize("n", [512, 1024, 2048])
+@pytest.mark.parametrize("fmt", ["CS16", "CU8", "CF32", "CU12", "CS4"])
+def test_rc_sizes_and_formats(engine, n, fmt):
+    tile = 65536 // n
+    width, hop = 3 * tile + 8, int(n * 0.37) + 1              # three full tiles + a remainder for the generic kernel
+    S = hop * (width - 1) + n + 3
+    buf = O.synth(fmt, 0, S, S, 0x5EC7B000 + n).tobytes()
+    run_both(engine, buf, fmt, n, width, "hann", want_db=False)
+    assert "render_rc_kernel" in engine.kernel_plan(fmt, n)
+
+
+@pytest.mark.parametrize("n", [512, 1024, 2048])
+def test_rc_hop_n_and_non_finite(engine, n):
+    tile = 65536 // n
+    width = 2 * tile
+    S = n * width
+    w, wt = O.window("blackmanHarris", n)
+    x = np.frombuffer(O.synth("CS16", 0, S, S, 0x5EC7B100 + n).tobytes(), "<i2").reshape(width, n, 2).copy()
+    x[5:9] = 0
+    x[tile + 3] = 0
+    buf = x.tobytes()
+    ora = O.render(buf, "CS16", n, width, w, 1 / wt, 6, 30, CM256, taps=True)
+    gpu = engine.render(buf, "CS16", n, width, w, 1 / wt, 6, 30, CM256)
+    check_parity(gpu, ora, CM256, n, width, False, None, f"rc n={n} silent frames")
+    assert gpu["cB_hist"][0] >= 5 * n and gpu["dBfs_min"] == -np.inf
+    f = np.frombuffer(O.synth("CF32", 0, S, S, 0x5EC7B200 + n).tobytes(), "<f4").reshape(width, n, 2).copy()
+    f[2, 100, 0] = np.nan
+    buf = f.tobytes()
+    with np.errstate(all="ignore"):
+        ora = O.render(buf, "CF32", n, width, w, 1 / wt, 0, 60, CM256, taps=True)
+    gpu = engine.render(buf, "CF32", n, width, w, 1 / wt, 0, 60, CM256)
+    check_parity(gpu, ora, CM256, n, width, False, None, f"rc n={n} NaN frame")
