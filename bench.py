@@ -199,18 +199,37 @@ def run_ours(args):
     eng.synth_fill(d_in.data_ptr(), FMT, sh["sample_first"], sh["sample_count"], total_samples, SEED)
     d_img = torch.empty(4 * width * N_FFT, dtype=torch.uint8, device=dev)
     d_g = torch.empty(3 * width, dtype=torch.uint8, device=dev)
-    # cB_hist | c_hist (u64 counters) | dBfs_min, dBfs_max: one buffer, so the multi-GPU merge is ONE all-gather
-    d_stats, d_hist, d_mm, d_gath = sharding.stats_buffers(torch, 1000 + len(cm), world, dev)
+    # cB_hist | c_hist (u64 counters) | dBfs_min, dBfs_max: one buffer, so the multi-GPU merge is ONE all-gather.
+    # Two sets: the all-gather of message i runs on its own stream while message i+1 renders (nothing in a render
+    # depends on the previous message's merged statistics); the timed region ends only when the last gather is done.
+    stats = [sharding.stats_buffers(torch, 1000 + len(cm), world, dev) for _ in range(2)]
+    coll_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    ev_render = [torch.cuda.Event() for _ in range(2)]
+    ev_coll = [torch.cuda.Event() for _ in range(2)]
+    state = {"i": 0}
     shard = sharding.shard_fields(sh, total_samples, SW, total_width) if world > 1 else None
 
     def step():
         rq, keep = eng.make_request(d_in.data_ptr(), FMT, N_FFT, width, w, 1.0 / wt, GAIN, RANGE, cm,
                                     byte_length=nbytes_in, shard=shard)
+        b = state["i"] & 1
+        state["i"] += 1
+        d_stats, d_hist, d_mm, d_gath = stats[b]
+        if world > 1:
+            stream.wait_event(ev_coll[b])                   # this buffer set was last gathered two messages ago
         rp = eng.render_enqueue(rq, d_img.data_ptr(), (d_g.data_ptr(), d_g.data_ptr() + width, d_g.data_ptr() + 2 * width),
                                 d_hist.data_ptr(), d_hist.data_ptr() + 8000, d_mm.data_ptr())
         if world > 1:                                       # the exchange step: one ~10 KB all-gather over NVLink
-            sharding.gather_stats(dist, d_stats, d_gath)
+            ev_render[b].record(stream)
+            with torch.cuda.stream(coll_stream):
+                coll_stream.wait_event(ev_render[b])
+                sharding.gather_stats(dist, d_stats, d_gath)
+                ev_coll[b].record(coll_stream)
         return rp
+
+    def join_collectives():
+        if world > 1:
+            stream.wait_event(ev_coll[0]); stream.wait_event(ev_coll[1])
 
     def barrier():
         if world > 1:
@@ -230,6 +249,7 @@ def run_ours(args):
     launches = 0
     for _ in range(args.steps):
         rp = step()
+    join_collectives()
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -254,6 +274,7 @@ def run_ours(args):
     value = total_samples / (ms_step * 1e-3) / 1e6
 
     # sanity of the timed output: histogram totals (size-independent property)
+    d_stats, d_hist, d_mm, d_gath = stats[(state["i"] - 1) & 1]        # the last message
     if world > 1:                                           # histograms add, min/max fold (lib/spectroplot.js:1229-1238)
         m_hist, m_min, m_max = sharding.fold_gathered(torch, d_gath, 1000 + len(cm))
     else:
