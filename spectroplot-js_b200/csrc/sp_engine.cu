@@ -365,7 +365,7 @@ extern "C" const char *sp_kernel_plan(sp_engine *e, int format, int n, int chann
     snprintf(buf, sizeof buf, "%s%srender_kernel<N=%d,%s> tile=%d frames smem_x=%d B%s", pl.sub_r > 1 ? "prepass_kernel<R=" : "",
              pl.sub_r > 1 ? (std::to_string(pl.sub_r) + "> + ").c_str() : "", 1 << pl.log2k,
              specialised(format) ? k_names[format] : "runtime-format", pl.tile, pl.smem_x * 8, channel_mode ? " +splitreal" : "");
-    if (pl.log2k >= 9 && pl.log2k <= 11 && !channel_mode && !getenv("SP_NO_FAST") && use_r64() && rc_for(format) && sp::sample_width(format) <= 8) {
+    if (pl.log2k >= 8 && pl.log2k <= 11 && !channel_mode && !getenv("SP_NO_FAST") && use_r64() && rc_for(format) && sp::sample_width(format) <= 8) {
         const size_t l = strlen(buf);
         snprintf(buf + l, sizeof buf - l, " | spectrogram fast path: render_rc_kernel<N=64x%d, tile=%d frames> (one exchange, joint histogram, TMA-staged input)",
                  (1 << pl.log2k) / 64, 65536 >> pl.log2k);
@@ -585,6 +585,14 @@ static bool fast_eligible(const Params &p)
     return !off && p.image && !p.waterfall && !p.channel_mode && !p.db_out && p.cmap_len <= 256 && (p.nframes % 8 == 0) &&
            (p.chunk_first % 8 == 0) && (((uintptr_t)p.image) & 31) == 0;
 }
+// render_r64_kernel / render_rc_kernel: any width (rows that are not 32-byte aligned are written word by word), so the
+// same frames take the same kernel whether a message is rendered in one piece, in pipeline chunks or in shards
+static bool fused_eligible(const Params &p)
+{
+    static const bool off = getenv("SP_NO_FAST") != nullptr;
+    return !off && p.image && !p.waterfall && !p.channel_mode && !p.db_out && p.cmap_len <= 256 && (p.chunk_first % 8 == 0) &&
+           (((uintptr_t)p.image) & 3) == 0;
+}
 // Frames [0, *nfast) of the chunk described by q go through the fast kernel: whole tiles of 8 frames that
 // lie entirely inside the buffer (the kernel carries no per-frame predicates); the caller renders the rest.
 static int launch_fast_kernel(sp_engine *e, fast_fn fn, Params &q, long long *nfast)
@@ -625,11 +633,12 @@ static int launch_fast_kernel(sp_engine *e, fast_fn fn, Params &q, long long *nf
     return SP_OK;
 }
 
-// Frames [0, *nfast) of the chunk described by q go through render_r64_kernel: whole tiles of 16 frames inside the buffer.
+// Frames [0, *nfast) of the chunk described by q go through render_r64_kernel: every group of 8 frames that lies inside the buffer
+// (the same frames whatever the chunking or sharding, so pipelined / sharded renders stay bit-identical to the single shot).
 static int launch_r64_kernel(sp_engine *e, r64_fn fn, Params &q, long long *nfast)
 {
     const bool sub = q.sub_r > 1;
-    long long nf = q.chunk_frames / 16 * 16;
+    long long nf = q.chunk_frames / 8 * 8;                 // the last tile may be partial (8 of 16 frames)
     if (!sub) {
         const long long sw = sp::sample_width(q.format);
         auto inside = [&](long long xr) {
@@ -638,7 +647,7 @@ static int launch_r64_kernel(sp_engine *e, r64_fn fn, Params &q, long long *nfas
             // the bulk copy reads whole 16-byte units: keep the rounded-up end inside the buffer's readable slack
             return p0 >= 0 && (unsigned long long)(p0 + 4096) * (unsigned long long)sw <= q.valid_bytes;
         };
-        while (nf > 0 && !inside(nf - 1)) nf -= 16;
+        while (nf > 0 && !inside(nf - 1)) nf -= 8;
         if (nf > 0 && !inside(0)) nf = 0;
     }
     *nfast = nf;
@@ -655,7 +664,7 @@ static int launch_r64_kernel(sp_engine *e, r64_fn fn, Params &q, long long *nfas
     unsigned *ctr = (unsigned *)e->tilectr.p + e->ctr_next++;
     Params r = q;
     r.chunk_frames = nf;
-    r.ntiles = (nf / 16) * (sub ? q.sub_r : 1);
+    r.ntiles = ((nf + 15) / 16) * (sub ? q.sub_r : 1);
     const int grid = (int)(r.ntiles < e->sm_count ? r.ntiles : e->sm_count);
     prof_begin(e);
     CU(fn(sub ? 1 : 0, &r, grid, e->stream, ctr, tw14, nullptr));
@@ -664,18 +673,18 @@ static int launch_r64_kernel(sp_engine *e, r64_fn fn, Params &q, long long *nfas
     return SP_OK;
 }
 
-// Frames [0, *nfast) of the chunk go through render_rc_kernel (N = 512 / 1024 / 2048): whole tiles of 65536 / N frames inside the buffer.
+// Frames [0, *nfast) of the chunk go through render_rc_kernel (N = 256 .. 2048): whole tiles of 65536 / N frames inside the buffer.
 static int launch_rc_kernel(sp_engine *e, rc_fn fn, int log2n, Params &q, long long *nfast)
 {
     const int n = 1 << log2n, tile = 65536 / n;
-    long long nf = q.chunk_frames / tile * tile;
+    long long nf = q.chunk_frames / 8 * 8;                 // the last tile may be partial (a multiple of 8 frames)
     const long long sw = sp::sample_width(q.format);
     auto inside = [&](long long xr) {
         const long long xgl = q.frame_first + q.chunk_first + xr;
         const long long p0 = (long long)(0.5 + q.stride * (double)xgl) - q.sample_base;       // lib/worker.js:72
         return p0 >= 0 && (unsigned long long)(p0 + n) * (unsigned long long)sw <= q.valid_bytes;
     };
-    while (nf > 0 && !inside(nf - 1)) nf -= tile;
+    while (nf > 0 && !inside(nf - 1)) nf -= 8;
     if (nf > 0 && !inside(0)) nf = 0;
     *nfast = nf;
     if (nf == 0) return SP_OK;
@@ -686,7 +695,7 @@ static int launch_rc_kernel(sp_engine *e, rc_fn fn, int log2n, Params &q, long l
     if (occ < 1) { *nfast = 0; return SP_OK; }
     Params r = q;
     r.chunk_frames = nf;
-    r.ntiles = nf / tile;
+    r.ntiles = (nf + tile - 1) / tile;
     const int grid = (int)(r.ntiles < e->sm_count ? r.ntiles : e->sm_count);
     prof_begin(e);
     CU(fn(log2n, &r, grid, e->stream, tw14, nullptr));
@@ -717,14 +726,14 @@ static int enqueue_frames(sp_engine *e, Job &j, Params &p)
     int occ = 0;
     if (j.plan.sub_r == 1) {
         Params q = p;
-        if (j.plan.log2k == 12 && fast_eligible(p) && use_r64() && r64_for(fmt) && (q.chunk_first % 16 == 0)) {
+        if (j.plan.log2k == 12 && fused_eligible(p) && use_r64() && r64_for(fmt)) {
             long long nfast = 0;
             int rc = launch_r64_kernel(e, r64_for(fmt), q, &nfast);
             if (rc) return rc;
             q.chunk_first += nfast;
             q.chunk_frames -= nfast;
         }
-        if (j.plan.log2k >= 9 && j.plan.log2k <= 11 && fast_eligible(p) && use_r64() && rc_for(fmt) && (q.chunk_first % 8 == 0)) {
+        if (j.plan.log2k >= 8 && j.plan.log2k <= 11 && fused_eligible(p) && use_r64() && rc_for(fmt)) {
             long long nfast = 0;
             int rc = launch_rc_kernel(e, rc_for(fmt), j.plan.log2k, q, &nfast);
             if (rc) return rc;
@@ -793,7 +802,7 @@ static int enqueue_frames(sp_engine *e, Job &j, Params &p)
             e->launches++;
             Params full = q;                                   // what the epilogue kernel sees
             if (tap) { q.spec_out = (float2 *)e->spec.p; q.image = nullptr; q.db_out = nullptr; q.channel_mode = 0; }
-            if (fast_eligible(q) && use_r64() && sp_r64_cf32 && (q.chunk_first % 16 == 0)) {
+            if (fused_eligible(q) && use_r64() && sp_r64_cf32) {
                 long long nfast = 0;
                 if ((rc = launch_r64_kernel(e, sp_r64_cf32, q, &nfast))) return rc;
                 q.sub_in += (size_t)nfast * (size_t)R * 4096;

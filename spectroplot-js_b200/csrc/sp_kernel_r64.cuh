@@ -53,6 +53,16 @@ __device__ __forceinline__ unsigned lut_at(unsigned lut_base, unsigned word, int
     return v;
 }
 
+// one row segment of 8 pixels: a 256-bit store when every image row is 32-byte aligned (width % 8 == 0), else 8 words
+__device__ __forceinline__ void store_row8(uint32_t *rowp, uint4 a, uint4 b, bool aligned)
+{
+    if (aligned) st_global_256(rowp, a, b);
+    else {
+        rowp[0] = a.x; rowp[1] = a.y; rowp[2] = a.z; rowp[3] = a.w;
+        rowp[4] = b.x; rowp[5] = b.y; rowp[6] = b.z; rowp[7] = b.w;
+    }
+}
+
 __device__ __forceinline__ void stream_barrier(int stream)
 {
     asm volatile("bar.sync %0, 64;" ::"r"(stream + 1) : "memory");
@@ -101,6 +111,7 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
 
     // t == 0 of a stream: start the bulk copy of chunk-relative frame xr (sub-sequence k0sub) into the stream's buffer
     auto stage = [&](long long xr, int k0sub, unsigned par) {
+        if (xr >= p.chunk_frames) xr = p.chunk_frames - 1;              // frames past the end of a partial tile redo the last one
         const void *src;
         unsigned bytes;
         if constexpr (SUB) {
@@ -134,6 +145,7 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
         // ================= store warps: staged colour bytes -> LUT -> image rows (lib/worker.js:115-121) =================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B::STORE_REGS));
         const int ht = tid - B::FFT_THREADS;
+        const bool rows_aligned = (p.nframes % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.image) & 31) == 0);
         for (; tile < p.ntiles; tile += gridDim.x, kk++) {
             const int k0sub = SUB ? (int)(tile % sub_r) : 0;
             const long long xr0 = tile_xr0(tile);
@@ -141,8 +153,9 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
             for (int h = 0; h < 2; h++) {
                 mbar_wait(s_full + h, kk & 1);
                 const size_t x0 = (size_t)(p.chunk_first + xr0) + 8 * h;
+                const bool live = xr0 + 8 * h < p.chunk_frames;        // partial last tile: chunk_frames is a multiple of 8
 #pragma unroll 1
-                for (int i = 0; i < 8; i++) {
+                for (int i = 0; i < (live ? 8 : 0); i++) {
                     // bins k0 + 64*(4m + j), j = 0..3, of the half's 8 frames: one 32-byte sector per row
                     const int id = ht + B::STORE_THREADS * i, k0 = id & 63, m = id >> 6;
                     const unsigned *src = s_stage + (8 * h) * B::ST_PITCH + m * 64 + k0;
@@ -160,10 +173,10 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
                             a.x = lut_at(lut_base, w[0], j); a.y = lut_at(lut_base, w[1], j); a.z = lut_at(lut_base, w[2], j); a.w = lut_at(lut_base, w[3], j);
                             b.x = lut_at(lut_base, w[4], j); b.y = lut_at(lut_base, w[5], j); b.z = lut_at(lut_base, w[6], j); b.w = lut_at(lut_base, w[7], j);
                         } else { a = make_uint4(w[0], w[1], w[2], w[3]); b = make_uint4(w[4], w[5], w[6], w[7]); }
-                        if (!(p.dbg & 1)) st_global_256(rowp, a, b);
+                        if (!(p.dbg & 1)) store_row8(rowp, a, b, rows_aligned);
                     }
                 }
-                if (ht < 8) {
+                if (ht < 8 && live) {
                     // per-frame min / max of the half's frames, folded across the two warps of their stream, as dB
                     const int fl = 8 * h + ht;
                     const long long xl = p.chunk_first + xr0 + fl;
@@ -194,6 +207,10 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
 #pragma unroll 1
         for (int step = 0; step < B::STEPS; step++) {
             const int fl = step * B::STREAMS + s;                       // frame of the tile handled by this stream now
+            const bool valid = xr0 + fl < p.chunk_frames;               // false: past the end of a partial last tile (outputs suppressed)
+            // chunk_frames is a multiple of 8, so the frames past the end are exactly staging half 1 of the last tile: nobody
+            // reads that half, and their histogram atomics are pointed at it instead of being predicated pixel by pixel
+            const unsigned jbase = valid ? jh_base : jh_base + (smem_u32(s_stage + 8 * B::ST_PITCH) - smem_u32(s_jh));
             int half = step >> 1;                                       // staging half of this frame
             // (opaque to the optimiser: with `step & 1` known, nvcc 12.9 folded 8*(step >> 1) into 4*step and
             // produced a misaligned mbarrier address)
@@ -209,7 +226,7 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
 #pragma unroll
                 for (int a = 0; a < 64; a++) v[a] = cpk(decode_raw<FMT>(rp, T * a + t, p.format));
                 // raw sample at p0 + n/2 (lib/worker.js:131-133); the power-of-two scale is exact
-                if (t == 0) p.fmid[p.chunk_first + xr0 + fl] = make_float2(cre(v[32]) * raw_scale<FMT>(), cim(v[32]) * raw_scale<FMT>());
+                if (t == 0 && valid) p.fmid[p.chunk_first + xr0 + fl] = make_float2(cre(v[32]) * raw_scale<FMT>(), cim(v[32]) * raw_scale<FMT>());
                 const float4 *wrow = reinterpret_cast<const float4 *>(s_win + t * B::WIN_PITCH);
 #pragma unroll
                 for (int q = 0; q < 16; q++) {
@@ -288,7 +305,7 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
                     const float l2 = fast_log2(abs2);
                     float Y;
                     const float S = jh_eval(l2, jc, Y);          // 2^23 + joint index, 2^23 + (cmax - colour index)
-                    red_shared_inc_addr(jh_base + (__float_as_uint(S) << 2));
+                    red_shared_inc_addr(jbase + (__float_as_uint(S) << 2));
                     yb[j] = __float_as_uint(Y);
                 }
                 // bins t + 64*(4m .. 4m+3) of frame fl: four colour bytes in one word
@@ -324,7 +341,7 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
                 nnan = __reduce_add_sync(0xffffffffu, nnan);
                 umn = __reduce_min_sync(0xffffffffu, __float_as_uint(mn));
                 umx = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
-                if ((t & 31) == 0) {
+                if ((t & 31) == 0 && valid) {
                     if (nzero) atomicAdd(&s_jh[JH_ZERO], nzero);
                     if (nbad) atomicAdd(&s_jh[JH_BAD], nbad);
                     if (nnan) {                 // NaN pixels were counted under the joint index sat(NaN) = 0 yields: move them

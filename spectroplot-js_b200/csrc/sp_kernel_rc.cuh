@@ -1,4 +1,4 @@
-// sp_kernel_rc.cuh — the 64-points-per-thread render kernel for N = 64 * C, C = 8, 16, 32 (N = 512, 1024, 2048).
+// sp_kernel_rc.cuh — the 64-points-per-thread render kernel for N = 64 * C, C = 4, 8, 16, 32 (N = 256 .. 2048).
 //
 // Same machine as render_r64_kernel (sp_kernel_r64.cuh), with the frame folded differently:
 //   * N = 64 x C: C threads transform a frame, each holding 64 complex points: dft<64> over the slow input digit
@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(384, 1) render_rc_kernel(const Params p, const
         unsigned bytes[FS];
 #pragma unroll
         for (int i = 0; i < FS; i++) {
-            const long long xgl = p.frame_first + p.chunk_first + xr + i;
+            const long long xc = xr + i < p.chunk_frames ? xr + i : p.chunk_frames - 1;   // partial last tile: redo the last frame
+            const long long xgl = p.frame_first + p.chunk_first + xc;
             const long long p0 = (long long)__dadd_rn(0.5, __dmul_rn(p.stride, (double)xgl)) - p.sample_base;   // lib/worker.js:72
             const unsigned long long off = (unsigned long long)p0 * B::SWB, a0 = off & ~15ull;
             src[i] = p.buf + a0;
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(384, 1) render_rc_kernel(const Params p, const
         // ================= store warps: staged colour bytes -> LUT -> image rows (lib/worker.js:115-121) =================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B::STORE_REGS));
         const int ht = tid - B::FFT_THREADS;
+        const bool rows_aligned = (p.nframes % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.image) & 31) == 0);
         for (; tile < p.ntiles; tile += gridDim.x, kk++) {
             const long long xr0 = tile * F;
 #pragma unroll 1
@@ -157,6 +159,7 @@ __global__ void __launch_bounds__(384, 1) render_rc_kernel(const Params p, const
                     const int wq = rest % (N / 4), g2 = rest / (N / 4);
                     const int grp = g2 * B::G + g;
                     const int tc = wq % C, r = (wq / C) % RPT, m = wq / 64;
+                    if (xr0 + HF * h + 8 * grp >= p.chunk_frames) continue;       // partial last tile (chunk_frames % 8 == 0)
                     const unsigned *src = half + (8 * grp) * B::FPW + wq;
                     unsigned w[8];
 #pragma unroll
@@ -169,11 +172,12 @@ __global__ void __launch_bounds__(384, 1) render_rc_kernel(const Params p, const
                         uint4 a, b;
                         a.x = lut_at(lut_base, w[0], j); a.y = lut_at(lut_base, w[1], j); a.z = lut_at(lut_base, w[2], j); a.w = lut_at(lut_base, w[3], j);
                         b.x = lut_at(lut_base, w[4], j); b.y = lut_at(lut_base, w[5], j); b.z = lut_at(lut_base, w[6], j); b.w = lut_at(lut_base, w[7], j);
-                        st_global_256(rowp, a, b);
+                        store_row8(rowp, a, b, rows_aligned);
                     }
                 }
                 for (int fl = ht; fl < HF; fl += B::STORE_THREADS) {
                     // per-frame min / max of the half's frames as dB
+                    if (xr0 + HF * h + fl >= p.chunk_frames) break;
                     const long long xl = p.chunk_first + xr0 + HF * h + fl;
                     const uint2 mm = s_mm[HF * h + fl];
                     p.fmin[xl] = fminf(0.0f, fmaf(fast_log2(__uint_as_float(mm.x)), p.c1, p.c0));        // lib/worker.js:82,102
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(384, 1) render_rc_kernel(const Params p, const
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(B::FFT_REGS));
     unsigned fpar = 0;                      // parity of this stream's step counter (mbarrier phase, s_off slot)
     if (ts == 0 && tile < p.ntiles) stage(tile * F + s * FS, 0);
-    constexpr unsigned GROUP_BASE_MASK = C == 32 ? 0xffffffffu : (C == 16 ? 0xffffu : 0xffu);
+    constexpr unsigned GROUP_BASE_MASK = C == 32 ? 0xffffffffu : ((1u << (C & 31)) - 1u);
     const unsigned gmask = GROUP_BASE_MASK << ((ts & 31) / C * C);               // lanes of this frame
 
     while (tile < p.ntiles) {
@@ -198,6 +202,8 @@ __global__ void __launch_bounds__(384, 1) render_rc_kernel(const Params p, const
 #pragma unroll 1
         for (int step = 0; step < B::STEPS; step++) {
             const int fl = step * B::SF + s * FS + fi;                  // frame of the tile handled by this thread now
+            const bool valid = xr0 + fl < p.chunk_frames;               // false: past the end of a partial last tile (outputs suppressed)
+            const unsigned dump = smem_u32(s_jh + JH_SIZE - 1);         // histogram atomics of such frames land in an unused counter
             int half = step >> 1;                                       // staging half of this step
             asm volatile("" : "+r"(half));                              // (see render_r64_kernel: keeps nvcc from folding 8*(step >> 1))
             cf v[64];
@@ -208,7 +214,7 @@ __global__ void __launch_bounds__(384, 1) render_rc_kernel(const Params p, const
 #pragma unroll
                 for (int a = 0; a < 64; a++) v[a] = cpk(decode_raw<FMT>(rp, C * a + t, p.format));
                 // raw sample at p0 + n/2 (lib/worker.js:131-133); the power-of-two scale is exact
-                if (t == 0) p.fmid[p.chunk_first + xr0 + fl] = make_float2(cre(v[32]) * raw_scale<FMT>(), cim(v[32]) * raw_scale<FMT>());
+                if (t == 0 && valid) p.fmid[p.chunk_first + xr0 + fl] = make_float2(cre(v[32]) * raw_scale<FMT>(), cim(v[32]) * raw_scale<FMT>());
                 const float4 *wrow = reinterpret_cast<const float4 *>(s_win + t * 64);
 #pragma unroll
                 for (int q = 0; q < 16; q++) {
@@ -291,7 +297,7 @@ __global__ void __launch_bounds__(384, 1) render_rc_kernel(const Params p, const
                         const float l2 = fast_log2(abs2);
                         float Y;
                         const float S = jh_eval(l2, jc, Y);
-                        red_shared_inc_addr(jh_base + (__float_as_uint(S) << 2));
+                        red_shared_inc_addr(valid ? jh_base + (__float_as_uint(S) << 2) : dump);
                         yb[j] = __float_as_uint(Y);
                     }
                     // bins (t*RPT + r) + 64*(4m .. 4m+3): four colour bytes in one word at m*64 + r*C + t
@@ -319,6 +325,7 @@ __global__ void __launch_bounds__(384, 1) render_rc_kernel(const Params p, const
                     mn = fminf(mn, abs2 < 1.17549435e-38f ? 0.0f : abs2);
                     mx = fmaxf(mx, abs2);
                 }
+                if (!valid) nzero = nbad = nnan = 0;
                 nzero = __reduce_add_sync(0xffffffffu, nzero);
                 nbad = __reduce_add_sync(0xffffffffu, nbad);
                 nnan = __reduce_add_sync(0xffffffffu, nnan);

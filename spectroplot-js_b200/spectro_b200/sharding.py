@@ -17,9 +17,12 @@ def plan_shards(total_samples: int, n: int, total_width: int, world: int, align_
     sample_first is rounded down to `align_samples` so any format's byte offset is 16-byte aligned."""
     stride = (total_samples - n) / (total_width - 1)
     out = []
+    # shard boundaries on multiples of 8 frames: the fused kernels write whole 32-byte sectors (8 frames of a row), so
+    # every frame keeps the kernel - and therefore the exact fp32 arithmetic - it has in the unsharded message
+    cut = lambda g: total_width if g >= world else (g * total_width // world) // 8 * 8
     for g in range(world):
-        x0 = g * total_width // world
-        x1 = (g + 1) * total_width // world
+        x0 = cut(g)
+        x1 = cut(g + 1)
         if x1 <= x0:
             out.append(dict(frame_first=x0, width=0, sample_first=0, sample_count=0))
             continue

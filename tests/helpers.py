@@ -70,8 +70,10 @@ def check_parity(gpu, ora, cmap, n, width, waterfall=False, gpu_db=None, label="
         assert d.max() <= 1, f"{label}: {k} max diff {d.max()}"
     for k in ("dBfs_min", "dBfs_max"):
         a, b = gpu[k], getattr(ora, k)
-        if np.isfinite(b) and b > DB_FLOOR_REF:
+        if np.isfinite(b) and b > DB_FLOOR_STRICT:
             assert abs(a - b) <= DB_TOL, f"{label}: {k} {a} vs {b}"
+        elif np.isfinite(b) and b > DB_FLOOR_REF:            # a single bin of the -120..-100 dBFS band (see db_error_stats)
+            assert abs(a - b) <= DB_TOL_FLOOR_MAX, f"{label}: {k} {a} vs {b}"
         elif np.isfinite(b):
             assert abs(a - b) <= 1.0, f"{label}: {k} {a} vs {b}"
         else:
