@@ -267,6 +267,10 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
             const long long xl = p.chunk_first + xr;                      // local frame == image column
             cf v[P];
             bool ragged = false;                                          // frame reads past the end of the buffer
+            // two-pass sizes (N <= 256): a slot's T <= 16 threads sit in one warp and the only barrier of a frame is the one
+            // between the pass-A writes and the last-pass reads of bufA; order this frame's writes after the previous
+            // frame's reads explicitly (compute-sanitizer racecheck flagged the intra-warp write-after-read)
+            if constexpr (C::PASSES == 2) __syncwarp();
             // ---------------- load + decode + window (lib/worker.js:70-75) ----------------
             if (sub) {
                 const float2 *src = p.sub_in + ((size_t)xr * sub_r + k0sub) * N;

@@ -74,8 +74,8 @@ def check_parity(gpu, ora, cmap, n, width, waterfall=False, gpu_db=None, label="
             assert abs(a - b) <= DB_TOL, f"{label}: {k} {a} vs {b}"
         elif np.isfinite(b) and b > DB_FLOOR_REF:            # a single bin of the -120..-100 dBFS band (see db_error_stats)
             assert abs(a - b) <= DB_TOL_FLOOR_MAX, f"{label}: {k} {a} vs {b}"
-        elif np.isfinite(b):
-            assert abs(a - b) <= 1.0, f"{label}: {k} {a} vs {b}"
+        elif np.isfinite(b):          # below -120 dBFS both values are round-off (float64 there, fp32 here): only "below the floor"
+            assert a <= DB_FLOOR_REF + DB_TOL_FLOOR_MAX, f"{label}: {k} {a} vs {b}"
         else:
             assert a == b, f"{label}: {k} {a} vs {b}"
     if gpu_db is not None:

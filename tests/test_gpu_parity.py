@@ -480,3 +480,18 @@ def test_rc_hop_n_and_non_finite(engine, n):
         ora = O.render(buf, "CF32", n, width, w, 1 / wt, 0, 60, CM256, taps=True)
     gpu = engine.render(buf, "CF32", n, width, w, 1 / wt, 0, 60, CM256)
     check_parity(gpu, ora, CM256, n, width, False, None, f"rc n={n} NaN frame")
+
+
+def test_repeated_renders_are_bit_identical(engine):
+    """Race detector of last resort: the fused kernels hand tiles between warpgroups through mbarriers (which
+    compute-sanitizer racecheck does not model); twelve renders of the same message must agree to the last byte and count."""
+    for fmt, n, width in (("CS16", 4096, 64), ("CU8", 1024, 200), ("CS4", 128, 300), ("CF32", 8192, 24)):
+        S = n * (width // 2) + 999
+        buf = O.synth(fmt, 0, S, S, 0x5EC7A000 + n).tobytes()
+        w, wt = O.window("hann", n)
+        first = engine.render(buf, fmt, n, width, w, 1 / wt, 6, 30, CM256)
+        for _ in range(11):
+            again = engine.render(buf, fmt, n, width, w, 1 / wt, 6, 30, CM256)
+            for k in ("image", "cB_hist", "c_hist", "gauge_mins", "gauge_maxs", "gauge_amps"):
+                assert np.array_equal(first[k], again[k]), (fmt, n, k)
+            assert first["dBfs_min"] == again["dBfs_min"] and first["dBfs_max"] == again["dBfs_max"]

@@ -30,7 +30,7 @@ def main():
     cases.append(("C1", "CU8", 1024, 1, "hann", "cube1", 1 << 26))
     cases.append(("C2", "CS16", 4096, 1, "blackmanHarris", "viridis", 100 << 20))
     cases.append(("C2-hann", "CS16", 4096, 1, "hann", "viridis", 100 << 20))
-    for z in (2, 4):
+    for z in (2, 4, 8):
         cases.append((f"C2-z{z}", "CS16", 4096, z, "hann", "viridis", 1 << 26))
     for z in (1, 2, 4, 8):
         cases.append((f"C3-z{z}", "CF32", 32768, z, "hann", "inferno", 1 << 27))
