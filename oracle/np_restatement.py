@@ -1,7 +1,7 @@
 """Second, independent float64 restatement of the render worker in numpy.
 
-TEST INFRASTRUCTURE ONLY (see oracle/spectro_oracle.c).  PARITY UNPINNED for the same
-reason.  This one is vectorised and uses numpy's pocketfft instead of the reference's
+TEST INFRASTRUCTURE ONLY (see oracle/spectro_oracle.c).  The parity pin is described there
+(reference source run by oracle/jsmini.py -> tests/golden/ref_js/).  This one is vectorised and uses numpy's pocketfft instead of the reference's
 radix-2 transform, so an error in either restatement of lib/fft_nayuki.js / lib/worker.js
 shows up as a disagreement between the two.  It also generates tests/golden/*.npz
 (tools/make_golden.py).

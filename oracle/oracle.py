@@ -4,8 +4,9 @@ TEST INFRASTRUCTURE ONLY — see the header of spectro_oracle.c.  Imported by te
 __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs; never by
 the product path under spectroplot-js_b200/.
 
-PARITY UNPINNED: the reference has no tests / golden vectors and cannot be executed here
-(no JavaScript engine in the image).
+PARITY PIN: the reference has no tests / golden vectors and the image has no JavaScript engine; the pin
+is the reference's own source executed by oracle/jsmini.py (tools/make_ref_golden.py ->
+tests/golden/ref_js/), which this oracle reproduces exactly (tests/test_reference_js.py).
 """
 from __future__ import annotations
 

@@ -6,13 +6,20 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * use it, and only as the checker / the CPU arm.
  *
- * PARITY UNPINNED: the reference (triq-org/spectroplot-js v1.2.1) ships no tests,
- * golden vectors or fixtures for this path, and no JavaScript engine exists in
- * this image, so the reference itself cannot be executed.  This file restates
- * the reference line by line (citations below are reference file:line); it is
- * cross-checked against (i) the derived known-answers of SURVEY.md Appendix B,
- * (ii) an independent numpy restatement (oracle/np_restatement.py, different
- * FFT), and (iii) mathematical identities (naive DFT, full-scale tone == 0 dB).
+ * PARITY PIN: the reference (triq-org/spectroplot-js v1.2.1) ships no tests, golden
+ * vectors or fixtures for this path, and no JavaScript engine exists in this image.
+ * The pin is therefore the reference's own SOURCE executed by oracle/jsmini.py (an
+ * ES-subset interpreter written for this purpose): tools/make_ref_golden.py runs the
+ * unmodified lib/worker.js (+ samples.js, fft_nayuki.js, windows.js, the cmap modules)
+ * on 36 messages and commits the replies under tests/golden/ref_js/;
+ * tests/test_reference_js.py requires this file to reproduce every reply EXACTLY
+ * (image bytes, both histograms, gauges, dBfs_min / dBfs_max).  Residual caveat: jsmini
+ * takes Math.log10 / cos / sin from the platform libm where V8 uses its fdlibm port
+ * (<= 1 ulp, visible only at exact quantisation ties).  Further cross-checks:
+ * (i) the derived known-answers of SURVEY.md Appendix B, (ii) an independent numpy
+ * restatement (oracle/np_restatement.py, different FFT), (iii) mathematical identities
+ * (naive DFT, full-scale tone == 0 dB).  This file restates the reference line by line
+ * (citations below are reference file:line).
  *
  * All arithmetic is IEEE double like JavaScript numbers.  Build with
  * -ffp-contract=off so no FMA contraction changes the operation order.

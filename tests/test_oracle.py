@@ -1,8 +1,9 @@
 """CPU tests of the oracle (test infrastructure) — runs without a GPU.
 
-The reference has no tests; the pins are SURVEY.md Appendix B (derived known-answers), the
-agreement of two independent restatements (C radix-2 vs numpy pocketfft), mathematical
-identities, and the committed golden fixtures."""
+The reference has no tests.  The primary pin is tests/test_reference_js.py (replies of the reference's own source,
+run by oracle/jsmini.py); this file holds the secondary ones: SURVEY.md Appendix B (derived known-answers), the
+agreement of two independent restatements (C radix-2 vs numpy pocketfft), mathematical identities, and the
+restatement-generated golden fixtures."""
 import glob
 import os
 import struct

@@ -1,9 +1,10 @@
 """Generate tests/golden/*.npz: small input/output vectors for the render path.
 
-The reference cannot be executed here (no JavaScript engine), so the vectors come from the
+These vectors come from the
 independent numpy restatement (oracle/np_restatement.py) and are cross-checked against the C
 restatement before being written; SURVEY.md Appendix B's derived known-answers are stored too.
-PARITY UNPINNED (no upstream golden vectors exist).  Re-run:  python tools/make_golden.py
+These are restatement-vs-restatement vectors; the pins against the reference's own code are
+tests/golden/ref_js/ (tools/make_ref_golden.py).  Re-run:  python tools/make_golden.py
 """
 import os, sys
 import numpy as np
