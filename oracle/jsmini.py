@@ -137,7 +137,7 @@ class JSArrayBuffer(JSObject):
 
 TYPED = {"Uint8Array": np.uint8, "Int8Array": np.int8, "Uint16Array": np.uint16, "Int16Array": np.int16,
          "Uint32Array": np.uint32, "Int32Array": np.int32, "Float32Array": np.float32, "Float64Array": np.float64,
-         "Uint8ClampedArray": np.uint8}
+         "Uint8ClampedArray": np.uint8, "BigUint64Array": np.uint64, "BigInt64Array": np.int64}
 
 
 class JSTypedArray(JSObject):
@@ -693,6 +693,22 @@ class Parser:
         kind = self.next().v
         decls = []
         while True:
+            if self.is_p("{"):                      # const { a, b: c } = expr
+                self.next()
+                names = []
+                while not self.eat_p("}"):
+                    key = self.next().v
+                    alias = key
+                    if self.eat_p(":"):
+                        alias = self.expect_id()
+                    names.append((key, alias))
+                    if not self.is_p("}"):
+                        self.expect_p(",")
+                self.expect_p("=")
+                decls.append((tuple(names), self.assignment()))
+                if not self.eat_p(","):
+                    break
+                continue
             name = self.expect_id()
             init = None
             if self.eat_p("="):
@@ -1097,7 +1113,8 @@ def collect_hoists(stmts, top=True):
             return
         k = s[0]
         if k == "var" and s[1] == "var":
-            names.extend(n for n, _ in s[2])
+            for n, _ in s[2]:
+                names.extend([a for _k, a in n] if isinstance(n, tuple) else [n])
         elif k == "funcdecl" and top_level:
             funcs.append((s[1], s[2]))
         elif k == "block":
@@ -1380,6 +1397,18 @@ class Interp:
         if k == "var":
             kind = s[1]
             decls = [(n, self.c_expr(i) if i is not None else None) for n, i in s[2]]
+            if any(isinstance(n, tuple) for n, _ in decls):
+                get_prop = self.get_prop
+
+                def run_destruct(env):
+                    for n, i in decls:
+                        if isinstance(n, tuple):
+                            o = i(env)
+                            for key, alias in n:
+                                env.vars[alias] = get_prop(o, key)
+                        else:
+                            env.vars[n] = i(env) if i is not None else UNDEF
+                return run_destruct
             if kind == "var":
                 def run_var(env):
                     for n, i in decls:
@@ -1613,7 +1642,7 @@ class Interp:
             d = s[1]
             run = self.c_stmt(d)
             if d[0] == "var":
-                names = [n for n, _ in d[2]]
+                names = [x for n, _ in d[2] for x in ([a for _k, a in n] if isinstance(n, tuple) else [n])]
             else:
                 names = [d[1]]
 
@@ -2012,6 +2041,44 @@ class Interp:
             self.run_source(f.read(), path, os.path.dirname(path), env)
         return ex
 
+    def drain(self):
+        """Run queued promise reactions (microtasks) until none is left."""
+        n = 0
+        while self.jobs:
+            fn, v = self.jobs.pop(0)
+            fn(v)
+            n += 1
+        return n
+
+    def promise_state(self, p):
+        return p.state, p.value
+
+    def require_file(self, path, require=None):
+        """CommonJS module: `require`, `module`, `exports` in scope; returns module.exports."""
+        path = os.path.normpath(path)
+        if path in self.modules:
+            return self.modules[path]["exports"]
+        mod = JSObject(self.object_proto)
+        mod.props["exports"] = JSObject(self.object_proto)
+        self.modules[path] = mod.props
+        env = Scope(self.globals)
+        env.vars["module"] = mod
+        env.vars["exports"] = mod.props["exports"]
+        base = os.path.dirname(path)
+
+        def req(this, a):
+            spec = js_to_string(a[0])
+            if require is not None:
+                r = require(spec)
+                if r is not None:
+                    return r
+            p2 = os.path.join(base, spec)
+            return self.require_file(p2 if os.path.exists(p2) else p2 + ".js", require)
+        env.vars["require"] = NativeFunction(self, "require", req)
+        with open(path) as f:
+            self.run_source(f.read(), path, base, env)
+        return mod.props["exports"]
+
     def native_instanceof(self, a, b):
         nm = b.name
         if nm == "Array":
@@ -2024,6 +2091,8 @@ class Interp:
             return isinstance(a, JSObject)
         if nm == "Function":
             return isinstance(a, (JSFunction, NativeFunction))
+        if nm == "Promise":
+            return isinstance(a, self.JSPromise)
         return False
 
     # ---- host helpers
@@ -2377,6 +2446,7 @@ def _install_builtins(I):
             return JSTypedArray(I, kind, buf, np.frombuffer(buf.data, dtype=dt))
         f = native(kind, lambda t, a: make(a), make)
         f.props["BYTES_PER_ELEMENT"] = dt.itemsize
+        f.props["from"] = native("from", lambda t, a: make([array_from(None, a)]))
         return f
     for kind in TYPED:
         G[kind] = typed_ctor(kind)
@@ -2390,6 +2460,12 @@ def _install_builtins(I):
         return JSTypedArray(I, t.kind, t.buffer, t.arr[s:e])
 
     def ta_set(t, a):
+        if isinstance(a[0], JSTypedArray) and a[0].kind == t.kind:
+            off = int(to_number(arg(a, 1, 0)))
+            if off + len(a[0].arr) > len(t.arr):
+                raise JSThrow("RangeError: offset is out of bounds")
+            t.arr[off:off + len(a[0].arr)] = a[0].arr
+            return UNDEF
         src, off = I.iterate(a[0]), int(to_number(arg(a, 1, 0)))
         for i, v in enumerate(src):
             I.set_prop(t, off + i, v)
@@ -2491,16 +2567,96 @@ def _install_builtins(I):
     for nm in ("Error", "TypeError", "RangeError", "ReferenceError", "SyntaxError"):
         G[nm] = err_ctor(nm)
 
-    def promise_resolved(v):
-        p = JSObject(I.object_proto)
-        p.props["then"] = native("then", lambda t, a: promise_resolved(I.call(a[0], UNDEF, [v])) if a and a[0] is not UNDEF else t)
-        p.props["catch"] = native("catch", lambda t, a: t)
-        p.props["__value__"] = v
+    # Promise: settle + reaction jobs on a microtask queue that the host drains (Interp.drain) after each entry into JS
+    class JSPromise(JSObject):
+        __slots__ = ("state", "value", "reactions")
+
+        def __init__(self):
+            JSObject.__init__(self, promise_proto)
+            self.state, self.value, self.reactions = "pending", UNDEF, []
+    promise_proto = JSObject(I.object_proto)
+    I.jobs = []
+
+    def settle(p, state, v):
+        if p.state != "pending":
+            return
+        if state == "fulfilled" and isinstance(v, JSPromise):
+            subscribe(v, lambda x: settle(p, "fulfilled", x), lambda x: settle(p, "rejected", x))
+            return
+        p.state, p.value = state, v
+        for on_f, on_r in p.reactions:
+            I.jobs.append((on_f if state == "fulfilled" else on_r, v))
+        p.reactions = []
+
+    def subscribe(p, on_f, on_r):
+        if p.state == "pending":
+            p.reactions.append((on_f, on_r))
+        else:
+            I.jobs.append((on_f if p.state == "fulfilled" else on_r, p.value))
+
+    def promise_then(t, a):
+        on_f, on_r = arg(a, 0), arg(a, 1)
+        p2 = JSPromise()
+
+        def run(handler, fallback_state):
+            def job(v):
+                if isinstance(handler, (JSFunction, NativeFunction)):
+                    try:
+                        settle(p2, "fulfilled", handler.call(UNDEF, [v]))
+                    except JSThrow as ex:
+                        settle(p2, "rejected", ex.value)
+                else:
+                    settle(p2, fallback_state, v)
+            return job
+        subscribe(t, run(on_f, "fulfilled"), run(on_r, "rejected"))
+        return p2
+    promise_proto.props["then"] = native("then", promise_then)
+    promise_proto.props["catch"] = native("catch", lambda t, a: promise_then(t, [UNDEF, arg(a, 0)]))
+
+    def promise_construct(a):
+        p = JSPromise()
+        res = native("resolve", lambda t, x: (settle(p, "fulfilled", arg(x, 0)), UNDEF)[1])
+        rej = native("reject", lambda t, x: (settle(p, "rejected", arg(x, 0)), UNDEF)[1])
+        try:
+            I.call(a[0], UNDEF, [res, rej])
+        except JSThrow as ex:
+            settle(p, "rejected", ex.value)
         return p
-    P = native("Promise", lambda t, a: UNDEF)
-    P.props["resolve"] = native("resolve", lambda t, a: promise_resolved(arg(a, 0)))
-    P.props["all"] = native("all", lambda t, a: promise_resolved(JSArray(I, [I.get_prop(x, "__value__") for x in I.iterate(a[0])])))
+
+    def promise_resolve(t, a):
+        v = arg(a, 0)
+        if isinstance(v, JSPromise):
+            return v
+        p = JSPromise()
+        settle(p, "fulfilled", v)
+        return p
+
+    def promise_reject(t, a):
+        p = JSPromise()
+        settle(p, "rejected", arg(a, 0))
+        return p
+
+    def promise_all(t, a):
+        items = I.iterate(a[0])
+        p = JSPromise()
+        out, left = [UNDEF] * len(items), [len(items)]
+        if not items:
+            settle(p, "fulfilled", JSArray(I, []))
+        for i, it in enumerate(items):
+            def on_f(v, i=i):
+                out[i] = v
+                left[0] -= 1
+                if left[0] == 0:
+                    settle(p, "fulfilled", JSArray(I, out))
+            subscribe(promise_resolve(None, [it]), on_f, lambda v: settle(p, "rejected", v))
+        return p
+    P = native("Promise", lambda t, a: UNDEF, promise_construct)
+    P.props["prototype"] = promise_proto
+    P.props["resolve"] = native("resolve", promise_resolve)
+    P.props["reject"] = native("reject", promise_reject)
+    P.props["all"] = native("all", promise_all)
     G["Promise"] = P
+    I.JSPromise = JSPromise
     con = JSObject(I.object_proto)
     for nm in ("log", "warn", "error", "info", "debug", "time", "timeEnd"):
         con.props[nm] = native(nm, lambda t, a: (I.log.append(" ".join(js_to_string(x) for x in a)), UNDEF)[1])

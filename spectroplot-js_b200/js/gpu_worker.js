@@ -1,8 +1,10 @@
 /**
  * gpu_worker.js — worker-protocol shim over the N-API addon (spectro_napi.c).
  *
- * NOT EXERCISED IN THIS IMAGE (no Node.js).  Mirrors spectro_b200/worker.py, which is the tested
- * implementation of the same shim.  Hand the class to the reference as its worker constructor:
+ * There is no Node.js in the build image: this file is executed in the test suite by oracle/jsmini.py
+ * (tests/test_js_host.py) with the addon replaced by an object of the same three functions that calls the C ABI
+ * (GPU suite) or the oracle (CPU suite).  spectro_b200/worker.py is the Python mirror of the same shim.
+ * Hand the class to the reference as its worker constructor:
  *
  *     import { GpuWorker } from './gpu_worker.js'
  *     new Spectroplot({ ..., workerOrUrl: GpuWorker })     // reference lib/spectroplot.js:100-116
