@@ -1,7 +1,10 @@
 /*
  * spectro_napi.c — thin N-API addon over the C ABI (include/spectro_b200.h).
  *
- * NOT BUILT OR TESTED IN THIS IMAGE: there is no Node.js toolchain (no node, no node_api.h).
+ * There is no Node.js toolchain in the build image (no node, no node_api.h), so the test suite compiles this file
+ * against tests/napi_stub/node_api.h (the Node-API signatures it uses, -Wall -Wextra -Werror) and runs it on a small fake
+ * Node-API runtime (tests/napi_stub/fake_napi.c, tests/test_napi_addon.py): create / render / destroy are called as
+ * js/gpu_worker.js calls them and the outputs are checked against the reference-worker fixtures on the GPU.
  * It is the binding a maintainer of spectroplot-js adds so that lib/worker.js's renderFft(ctx)
  * (reference lib/worker.js:23-156) runs on the GPU; gpu_worker.js puts the worker message
  * protocol on top of it.  Build where Node is available:
