@@ -4,4 +4,4 @@ protocol above a C ABI; all arithmetic of the path runs in hand-written sm_100a 
 from ._lib import Engine, PinnedBuffer, SpError, FORMATS  # noqa: F401
 from .worker import GpuWorker, renderFft  # noqa: F401
 from .spectroplot import Spectroplot  # noqa: F401
-from . import windows, cmaps, sharding  # noqa: F401
+from . import windows, cmaps, sharding, ingest, egress  # noqa: F401

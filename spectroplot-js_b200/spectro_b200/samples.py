@@ -22,9 +22,11 @@ class SampleView:
         format = format.upper()
         self.format = format
         canon = _ALIASES.get(format, format)
-        if canon in _AUDIO:
-            raise NotImplementedError("compressed audio needs the browser's decodeAudioData (out of scope); "
-                                      "decode to CF32 first")
+        self.audio = canon in _AUDIO                      # lib/samples.js:141-148: decoded to interleaved CF32
+        if self.audio:
+            self.container = canon
+            canon = "CF32"
+            self.format = "CF32"                         # "force format on decompressed buffer"
         if canon not in _TABLE:
             canon = "CU8"                      # lib/samples.js:149-155: default to CU8
         self.canonical = canon
@@ -35,6 +37,15 @@ class SampleView:
             self.loadBuffer(buffer)
 
     def loadBuffer(self, buffer):
+        if self.audio:                                    # readAudio() + interleaved(), lib/samples.js:260-302
+            from .ingest import AUDIO_PCM, decode_wav
+            if self.container not in AUDIO_PCM:
+                raise NotImplementedError("%s needs the browser's decodeAudioData; decode to WAV or CF32 first" % self.container)
+            data, rate, _ch = decode_wav(bytes(buffer))
+            self.sampleRate = rate
+            self.buffer = data.tobytes()
+            self.sampleCount = len(data) // 2
+            return self
         buffer = bytes(buffer) if not isinstance(buffer, (bytes, bytearray, memoryview)) else buffer
         if len(buffer) % self.elementSize:
             raise ValueError("RangeError: byte length of typed array should be a multiple of %d" % self.elementSize)

@@ -93,8 +93,12 @@ class Spectroplot:
         return self.processData()
 
     def setData(self, filedata):                                              # :483-511
-        if isinstance(filedata, str):
-            raise NotImplementedError("URL loading needs XHR (out of scope); pass {fileBuffer, name, size, type}")
+        if isinstance(filedata, str):                                         # :486-487 loads a URL; headless: a local file
+            import os
+            if not os.path.exists(filedata):
+                raise NotImplementedError("URL loading needs XHR (out of scope); pass a local path or {fileBuffer, name, size, type}")
+            from .ingest import load_capture
+            filedata = load_capture(filedata)
         self.fileinfo = filedata
         self.buffer = filedata["fileBuffer"]
         self.sampleFormat = parseFormat(filedata.get("name", ""))
@@ -125,9 +129,9 @@ class Spectroplot:
         return self.processData()
 
     def processData(self):                                                    # :1096-1285
-        if not self.buffer:
+        if self.buffer is None or len(self.buffer) == 0:
             return None
-        if not self.sampleView or not self.sampleView.buffer:
+        if not self.sampleView or self.sampleView.buffer is None or len(self.sampleView.buffer) == 0:
             return None
         if self.inProcess:
             return self.inProcess                                             # single flight (:1099)
