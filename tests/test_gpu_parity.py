@@ -495,3 +495,44 @@ def test_repeated_renders_are_bit_identical(engine):
             for k in ("image", "cB_hist", "c_hist", "gauge_mins", "gauge_maxs", "gauge_amps"):
                 assert np.array_equal(first[k], again[k]), (fmt, n, k)
             assert first["dBfs_min"] == again["dBfs_min"] and first["dBfs_max"] == again["dBfs_max"]
+
+
+# ------------------------------------------------------------------ randomized sweep over the whole option space
+def _random_cases(count, seed):
+    rng = np.random.default_rng(seed)
+    fmts = list(O.FORMATS)
+    cases = []
+    for i in range(count):
+        n = int(2 ** rng.integers(3, 15))                       # 8 .. 16384
+        fmt = fmts[int(rng.integers(0, len(fmts)))]
+        width = int(rng.choice([2, 3, 7, 8, 9, 15, 16, 17, 24, 31, 33, 40, 64, 65, 100]))
+        if n >= 4096:
+            width = min(width, 24)
+        hop = float(rng.choice([0.0, 0.37, 1.0, 1.0, 2.5]))     # x n: all frames on one position ... skipping data
+        S = n + int(hop * n * (width - 1)) + int(rng.integers(0, 50))
+        window = O.WINDOWS[int(rng.integers(0, len(O.WINDOWS)))]
+        gain = int(rng.choice([-10, 0, 6, 20, 45]))
+        rng_db = int(rng.choice([6, 30, 60, 120, -30]))
+        cmap_len = int(rng.choice([2, 64, 256, 256, 300]))
+        chm = bool(rng.integers(0, 4) == 0)
+        wf = bool(rng.integers(0, 4) == 0)
+        ragged = int(rng.integers(0, 5) == 0)
+        cases.append((i, fmt, n, width, S, window, gain, rng_db, cmap_len, chm, wf, ragged))
+    return cases
+
+
+@pytest.mark.parametrize("case", _random_cases(72, 20261017), ids=lambda c: "r%02d-%s-n%d-w%d" % (c[0], c[1], c[2], c[3]))
+def test_randomized_option_sweep(engine, case):
+    """Seeded random points of (format, N, width, hop, window, gain, range, cmap length, channel mode, waterfall, ragged tail):
+    every one must meet the parity bars against the oracle (which equals the reference, tests/test_reference_js.py)."""
+    i, fmt, n, width, S, window, gain, rng_db, cmap_len, chm, wf, ragged = case
+    buf = O.synth(fmt, 0, S, S, 0x5EC7B000 + i).tobytes()
+    sw = O.SAMPLE_WIDTH[O.fmt_id(fmt)]
+    if ragged:                                               # drop a partial sample: keep the typed-array element size
+        elem = 1 if sw <= 3 else (2 if sw == 4 else (8 if fmt == "CF64" else 4))
+        if sw > elem:
+            buf = buf[:len(buf) - elem]
+    if len(buf) // sw < n:
+        pytest.skip("shorter than one frame")
+    run_both(engine, buf, fmt, n, width, window, gain, rng_db, injective_cmap(cmap_len), chm, wf, want_db=not chm,
+             label="random case %d" % i)
