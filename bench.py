@@ -143,7 +143,7 @@ def run_reference(args):
                                        "an upper bound on the JS worker's speed"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -202,9 +202,6 @@ def run_ours(args):
     numa = bind_to_gpu_numa_node(local) if world > 1 else None
     torch.cuda.set_device(local)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's "NCCL version ..." banner (printed at NCCL_DEBUG=VERSION and WARN) and any
-        # other NCCL debug output go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     eng = spectro_b200.Engine(local)
@@ -367,14 +364,35 @@ def run_ours(args):
                                  "dBfs_max": m_max if world > 1 else rp.dBfs_max}}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_sample()
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: keep the real stdout for it and send everything else written to fd 1 by
+    libraries (NCCL prints its version banner there) to stderr."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -150,9 +150,16 @@ int sp_sample_width(int format);   /* bytes per complex sample, <0 on bad format
 int sp_element_size(int format);   /* typed-array element size in bytes           */
 
 /* Create an engine on the listed CUDA devices (ndev >= 1; device_ids may be NULL
- * to mean device 0).  With ndev > 1 a whole message is split by frame range
- * across the devices and the histograms / min / max are merged with one NCCL
- * all-reduce.  Fails with SP_E_NO_DEVICE when no sm_100 GPU is present. */
+ * to mean devices 0 .. ndev-1).  With ndev > 1, sp_render() splits a whole
+ * host-buffer message by contiguous frame range (cuts on multiples of 8 frames,
+ * global frame positions, an n-sample halo per range) across the devices, one
+ * host thread per device, each device writing its column band / row block
+ * straight into the caller's image; the histograms and min / max are merged on
+ * the host like lib/spectroplot.js:1229-1238 (ndev x ~10 KB).  The result is
+ * the single-device result (bit-identical when the width is a multiple of 8).
+ * The other entry points (taps, memory helpers, sp_render_enqueue) address the
+ * first device; one process per GPU with an NCCL merge is the alternative
+ * layout (bench.py).  Fails with SP_E_NO_DEVICE when no sm_100 GPU is present. */
 int sp_create(sp_engine **out, const int *device_ids, int ndev);
 void sp_destroy(sp_engine *e);
 const char *sp_last_error(sp_engine *e); /* e may be NULL: last error of sp_create */

@@ -16,6 +16,7 @@
 #include <map>
 #include <string>
 #include <strings.h>
+#include <thread>
 #include <vector>
 
 using sp::Params;
@@ -99,7 +100,11 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+// where a shard's image goes inside the caller's [n][total width] picture (multi-device engines; spectrogram layout)
+struct Placement { long long pitch_frames; long long col0; };
+
 struct sp_engine {
+    std::vector<sp_engine *> subs;           // ndev > 1: one single-device engine per GPU; this object only dispatches
     int ndev = 1;
     int dev = 0;
     int sm_count = 0;
@@ -155,14 +160,44 @@ static int ensure(sp_engine *e, DevBuf &b, size_t bytes)
     return SP_OK;
 }
 
-extern "C" const char *sp_last_error(sp_engine *e) { return e ? e->err.c_str() : g_create_err.c_str(); }
+// entry points other than sp_render work on the first device of a multi-device engine (taps, memory helpers, plan)
+static sp_engine *dev0(sp_engine *e)
+{
+    if (e && !e->subs.empty()) { e->err.clear(); return e->subs[0]; }
+    return e;
+}
+
+extern "C" const char *sp_last_error(sp_engine *e)
+{
+    if (!e) return g_create_err.c_str();
+    if (!e->subs.empty() && e->err.empty()) return e->subs[0]->err.c_str();
+    return e->err.c_str();
+}
 
 extern "C" int sp_create(sp_engine **out, const int *device_ids, int ndev)
 {
     if (!out) return fail(nullptr, SP_E_INVAL, "sp_create: out is null");
     *out = nullptr;
     if (ndev < 1) ndev = 1;
-    if (ndev > 1) return fail(nullptr, SP_E_INVAL, "sp_create: one device per engine in this build; shard with sp_request.frame_first / total_width (one engine per GPU)");
+    if (ndev > 1) {                          // one sub-engine per device; sp_render shards whole messages across them
+        sp_engine *parent = new sp_engine();
+        parent->ndev = ndev;
+        for (int i = 0; i < ndev; i++) {
+            sp_engine *sub = nullptr;
+            const int d = device_ids ? device_ids[i] : i;
+            const int rc = sp_create(&sub, &d, 1);
+            if (rc) {
+                for (sp_engine *s2 : parent->subs) sp_destroy(s2);
+                delete parent;
+                return rc;                   // g_create_err holds the message
+            }
+            parent->subs.push_back(sub);
+        }
+        parent->dev = parent->subs[0]->dev;
+        parent->sm_count = parent->subs[0]->sm_count;
+        *out = parent;
+        return SP_OK;
+    }
     int count = 0;
     cudaError_t c = cudaGetDeviceCount(&count);
     if (c != cudaSuccess || count == 0)
@@ -192,6 +227,11 @@ extern "C" int sp_create(sp_engine **out, const int *device_ids, int ndev)
 extern "C" void sp_destroy(sp_engine *e)
 {
     if (!e) return;
+    if (!e->subs.empty()) {
+        for (sp_engine *sub : e->subs) sp_destroy(sub);
+        delete e;
+        return;
+    }
     cudaSetDevice(e->dev);
     cudaDeviceSynchronize();
     for (auto &kv : e->tw) cudaFree(kv.second);
@@ -219,6 +259,7 @@ extern "C" void sp_destroy(sp_engine *e)
 
 extern "C" int sp_set_stream(sp_engine *e, void *cuda_stream)
 {
+    e = dev0(e);
     if (!e) return SP_E_INVAL;
     e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
     return SP_OK;
@@ -357,6 +398,7 @@ static Plan make_plan(int log2n)
 
 extern "C" const char *sp_kernel_plan(sp_engine *e, int format, int n, int channel_mode)
 {
+    e = dev0(e);
     if (!e) return "";
     const int l = ilog2_exact(n);
     char buf[384];
@@ -879,7 +921,7 @@ static long long pipeline_chunk_frames(const sp_request *rq)
     return (rq->width >= 3 * ch) ? ch : 0;       // short messages: single shot
 }
 
-static int render_pipelined(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, long long ch, double sample_count)
+static int render_pipelined(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, long long ch, const Placement *pl)
 {
     const int n = rq->n, sw = sp::sample_width(rq->format);
     const long long W = rq->width;
@@ -945,8 +987,8 @@ static int render_pipelined(sp_engine *e, const sp_request *rq, sp_reply *rp, Jo
                 CU(cudaMemcpyAsync(rp->image + (size_t)4 * n * (size_t)(W - x0 - cw), e->pimg[b].p, (size_t)4 * n * cw,
                                    cudaMemcpyDeviceToHost, e->s_d2h));
             else                    // columns [x0, x0 + cw) of the [n][W] image (lib/worker.js:117)
-                CU(cudaMemcpy2DAsync(rp->image + 4 * x0, (size_t)4 * W, e->pimg[b].p, (size_t)4 * cw, (size_t)4 * cw, (size_t)n,
-                                     cudaMemcpyDeviceToHost, e->s_d2h));
+                CU(cudaMemcpy2DAsync(rp->image + 4 * (x0 + (pl ? pl->col0 : 0)), (size_t)4 * (pl ? pl->pitch_frames : W), e->pimg[b].p,
+                                     (size_t)4 * cw, (size_t)4 * cw, (size_t)n, cudaMemcpyDeviceToHost, e->s_d2h));
             CU(cudaEventRecord(e->ev_out[b], e->s_d2h));
         }
     }
@@ -957,7 +999,6 @@ static int render_pipelined(sp_engine *e, const sp_request *rq, sp_reply *rp, Jo
     if (rp->cB_hist) CU(cudaMemcpyAsync(rp->cB_hist, j.d_cb, 8 * SP_CB_HIST_SIZE, cudaMemcpyDeviceToHost, e->stream));
     if (rp->c_hist) CU(cudaMemcpyAsync(rp->c_hist, j.d_c, 8 * (size_t)rq->cmap_len, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->s_d2h));
-    (void)sample_count;
     return finish(e, rp);
 }
 
@@ -978,6 +1019,7 @@ static int finish(sp_engine *e, sp_reply *rp)
 extern "C" int sp_render_enqueue(sp_engine *e, const sp_request *rq, sp_reply *rp)
 {
     if (!e || !rq || !rp) return fail(e, SP_E_INVAL, "null argument");
+    if (!e->subs.empty()) return fail(e, SP_E_INVAL, "sp_render_enqueue works on device-resident buffers: use one engine per GPU");
     if (!(rq->flags & SP_F_BUFFER_ON_DEVICE) || !(rq->flags & SP_F_REPLY_ON_DEVICE))
         return fail(e, SP_E_INVAL, "sp_render_enqueue needs SP_F_BUFFER_ON_DEVICE | SP_F_REPLY_ON_DEVICE");
     Job j;
@@ -990,6 +1032,7 @@ extern "C" int sp_render_enqueue(sp_engine *e, const sp_request *rq, sp_reply *r
 
 extern "C" int sp_render_finish(sp_engine *e, sp_reply *rp)
 {
+    e = dev0(e);
     if (!e || !rp) return fail(e, SP_E_INVAL, "null argument");
     if (!e->pending) return fail(e, SP_E_INVAL, "no render enqueued");
     e->pending = false;
@@ -997,20 +1040,25 @@ extern "C" int sp_render_finish(sp_engine *e, sp_reply *rp)
     return finish(e, rp);
 }
 
-extern "C" int sp_render(sp_engine *e, const sp_request *rq, sp_reply *rp)
+static int render_one(sp_engine *e, const sp_request *rq, sp_reply *rp, const Placement *pl)
 {
-    if (!e || !rq || !rp) return fail(e, SP_E_INVAL, "null argument");
     Job j;
     const bool host_io = !(rq->flags & (SP_F_BUFFER_ON_DEVICE | SP_F_REPLY_ON_DEVICE));
     const long long ch = (host_io && rq->width > 0 && rq->n > 0 && rq->byte_length > 0) ? pipeline_chunk_frames(rq) : 0;
     j.pipelined = ch > 0;
     int rc = prepare(e, rq, rp, j, false, nullptr);
     if (rc) return rc;
-    if (j.pipelined) return render_pipelined(e, rq, rp, j, ch, 0.0);
+    if (j.pipelined) return render_pipelined(e, rq, rp, j, ch, pl);
     if ((rc = enqueue(e, j))) return rc;
     const size_t W = (size_t)rq->width;
     if (!(rq->flags & SP_F_REPLY_ON_DEVICE)) {
-        if (j.d_image) CU(cudaMemcpyAsync(rp->image, j.d_image, 4 * W * (size_t)rq->n, cudaMemcpyDeviceToHost, e->stream));
+        if (j.d_image) {
+            if (pl && !rq->waterfall)       // a column band of the caller's [n][pitch] picture
+                CU(cudaMemcpy2DAsync(rp->image + 4 * pl->col0, (size_t)4 * pl->pitch_frames, j.d_image, 4 * W, 4 * W, (size_t)rq->n,
+                                     cudaMemcpyDeviceToHost, e->stream));
+            else
+                CU(cudaMemcpyAsync(rp->image, j.d_image, 4 * W * (size_t)rq->n, cudaMemcpyDeviceToHost, e->stream));
+        }
         if (rp->gauge_mins) CU(cudaMemcpyAsync(rp->gauge_mins, j.d_gmin, W, cudaMemcpyDeviceToHost, e->stream));
         if (rp->gauge_maxs) CU(cudaMemcpyAsync(rp->gauge_maxs, j.d_gmax, W, cudaMemcpyDeviceToHost, e->stream));
         if (rp->gauge_amps) CU(cudaMemcpyAsync(rp->gauge_amps, j.d_gamp, W, cudaMemcpyDeviceToHost, e->stream));
@@ -1020,12 +1068,117 @@ extern "C" int sp_render(sp_engine *e, const sp_request *rq, sp_reply *rp)
     return finish(e, rp);
 }
 
+// ------------------------------------------------------------------ multi-device engine (sp_create with ndev > 1)
+// One whole message, host buffers in and out: the frames are cut into ndev contiguous ranges on multiples of 8 frames
+// (spectro_b200/sharding.py::plan_shards is the same plan), every device renders its range at the GLOBAL frame
+// positions from its byte range plus an n-sample halo - one host thread per device, each running the ordinary
+// single-device path (pipelined H2D / render / D2H) - and writes its column band (spectrogram) or row block
+// (waterfall) straight into the caller's picture.  The only exchange is the merge of the two histograms and min / max
+// (lib/spectroplot.js:1229-1238): ndev x ~10 KB, folded on the host.  (One process per GPU merges the same data with
+// one NCCL all-gather instead: bench.py, spectro_b200/sharding.py.)
+static int render_multi(sp_engine *e, const sp_request *rq, sp_reply *rp)
+{
+    if (rq->flags & (SP_F_BUFFER_ON_DEVICE | SP_F_REPLY_ON_DEVICE))
+        return fail(e, SP_E_INVAL, "a multi-device engine takes host buffers (a device buffer lives on one GPU)");
+    if (rq->total_width != 0 || rq->total_byte_length != 0)
+        return fail(e, SP_E_INVAL, "a multi-device engine shards whole messages itself: leave the shard fields zero");
+    const int G = (int)e->subs.size();
+    const int sw = (rq->format >= 0 && rq->format < SP_FORMAT_COUNT) ? sp::sample_width(rq->format) : 0;
+    const long long W = rq->width, n = rq->n;
+    auto delegate = [&]() {                  // too small to split, or invalid: the first device alone (same checks, same errors)
+        const int rc = render_one(e->subs[0], rq, rp, nullptr);
+        if (rc) e->err = e->subs[0]->err;
+        return rc;
+    };
+    if (sw <= 0 || n < SP_MIN_N || W < 16LL * G || !rq->buffer || (double)rq->byte_length / sw < (double)n) return delegate();
+    const double sc = (double)rq->byte_length / (double)sw;
+    const double stride = (sc - (double)n) / (double)(W - 1);                      // lib/worker.js:50, global
+    auto cut = [&](int g) { return g >= G ? W : (g * W / G) / 8 * 8; };
+    auto pos = [&](long long x) { return (long long)(0.5 + stride * (double)x); }; // lib/worker.js:72
+    struct Part { sp_request rq; sp_reply rp; Placement pl; std::vector<uint64_t> cb, c; int rc = 0; bool used = false; };
+    std::vector<Part> parts((size_t)G);
+    int last_used = -1;
+    for (int g = 0; g < G; g++) if (cut(g + 1) > cut(g)) last_used = g;
+    for (int g = 0; g < G; g++) {
+        const long long x0 = cut(g), x1 = cut(g + 1);
+        if (x1 <= x0) continue;
+        Part &pt = parts[(size_t)g];
+        pt.used = true;
+        long long s0 = pos(x0);
+        s0 -= s0 % 16;                                                             // any format's byte offset stays 16-byte aligned
+        const long long s1 = pos(x1 - 1) + n;
+        unsigned long long b0 = (unsigned long long)s0 * sw, b1 = (unsigned long long)s1 * sw;
+        if (b1 > rq->byte_length || g == last_used) b1 = rq->byte_length;          // a ragged tail travels with the last shard
+        if (b0 > b1) b0 = b1;
+        pt.rq = *rq;
+        pt.rq.buffer = (const uint8_t *)rq->buffer + b0;
+        pt.rq.byte_length = b1 - b0;
+        pt.rq.width = x1 - x0;
+        pt.rq.total_byte_length = rq->byte_length;
+        pt.rq.total_width = W;
+        pt.rq.frame_first = x0;
+        pt.rq.buffer_first_sample = (uint64_t)s0;
+        memset(&pt.rp, 0, sizeof pt.rp);
+        pt.pl = Placement{ W, x0 };
+        if (rp->image) pt.rp.image = rq->waterfall ? rp->image + (size_t)4 * n * (size_t)(W - x1) : rp->image;   // rows [W - x1, W - x0)
+        if (rp->gauge_mins) pt.rp.gauge_mins = rp->gauge_mins + x0;
+        if (rp->gauge_maxs) pt.rp.gauge_maxs = rp->gauge_maxs + x0;
+        if (rp->gauge_amps) pt.rp.gauge_amps = rp->gauge_amps + x0;
+        pt.cb.assign(SP_CB_HIST_SIZE, 0);
+        pt.c.assign((size_t)(rq->cmap_len > 0 ? rq->cmap_len : 1), 0);
+        pt.rp.cB_hist = pt.cb.data();
+        pt.rp.c_hist = pt.c.data();
+    }
+    std::vector<std::thread> threads;
+    for (int g = 0; g < G; g++)
+        if (parts[(size_t)g].used)
+            threads.emplace_back([&, g]() { Part &pt = parts[(size_t)g]; pt.rc = render_one(e->subs[(size_t)g], &pt.rq, &pt.rp, &pt.pl); });
+    for (auto &t : threads) t.join();
+    for (int g = 0; g < G; g++)
+        if (parts[(size_t)g].used && parts[(size_t)g].rc) {
+            e->err = "device " + std::to_string(e->subs[(size_t)g]->dev) + ": " + e->subs[(size_t)g]->err;
+            return parts[(size_t)g].rc;
+        }
+    // merge (lib/spectroplot.js:1229-1238): histograms add, min / max fold from the worker's initial values
+    if (rp->cB_hist) memset(rp->cB_hist, 0, 8 * SP_CB_HIST_SIZE);
+    if (rp->c_hist) memset(rp->c_hist, 0, 8 * (size_t)rq->cmap_len);
+    rp->dBfs_min = 0.0;
+    rp->dBfs_max = -200.0;
+    rp->device_ms = 0.0f;
+    rp->kernel_launches = 0;
+    for (int g = 0; g < G; g++) {
+        const Part &pt = parts[(size_t)g];
+        if (!pt.used) continue;
+        if (rp->cB_hist) for (int i = 0; i < SP_CB_HIST_SIZE; i++) rp->cB_hist[i] += pt.cb[(size_t)i];
+        if (rp->c_hist) for (int i = 0; i < rq->cmap_len; i++) rp->c_hist[i] += pt.c[(size_t)i];
+        if (pt.rp.dBfs_min < rp->dBfs_min) rp->dBfs_min = pt.rp.dBfs_min;
+        if (pt.rp.dBfs_max > rp->dBfs_max) rp->dBfs_max = pt.rp.dBfs_max;
+        if (pt.rp.device_ms > rp->device_ms) rp->device_ms = pt.rp.device_ms;
+        rp->kernel_launches += pt.rp.kernel_launches;
+    }
+    return SP_OK;
+}
+
+extern "C" int sp_render(sp_engine *e, const sp_request *rq, sp_reply *rp)
+{
+    if (!e || !rq || !rp) return fail(e, SP_E_INVAL, "null argument");
+    if (!e->subs.empty()) return render_multi(e, rq, rp);
+    return render_one(e, rq, rp, nullptr);
+}
+
 extern "C" int sp_render_zooms(sp_engine *e, const sp_request *rq, int nlevels, const int64_t *widths, sp_reply *replies)
 {
     if (!e || !rq || !widths || !replies || nlevels < 1) return fail(e, SP_E_INVAL, "null argument or nlevels < 1");
     if (!rq->buffer) return fail(e, SP_E_INVAL, "buffer is required");
     sp_request r = *rq;
     int rc;
+    if (!e->subs.empty()) {                                // every level is sharded across the devices like a single message
+        for (int i = 0; i < nlevels; i++) {
+            r.width = widths[i];
+            if ((rc = sp_render(e, &r, &replies[i]))) return rc;
+        }
+        return SP_OK;
+    }
     if (!(rq->flags & SP_F_BUFFER_ON_DEVICE)) {            // one upload shared by every level
         CU(cudaSetDevice(e->dev));
         if ((rc = ensure(e, e->zin, rq->byte_length + 16))) return rc;
@@ -1042,6 +1195,7 @@ extern "C" int sp_render_zooms(sp_engine *e, const sp_request *rq, int nlevels, 
 
 extern "C" int sp_render_db(sp_engine *e, const sp_request *rq, float *db)
 {
+    e = dev0(e);
     if (!e || !rq || !db) return fail(e, SP_E_INVAL, "null argument");
     const size_t cnt = (size_t)rq->width * (size_t)rq->n;
     int rc = ensure(e, e->db, cnt * 4);
@@ -1059,6 +1213,7 @@ extern "C" int sp_render_db(sp_engine *e, const sp_request *rq, float *db)
 
 extern "C" int sp_decode(sp_engine *e, int format, const void *bytes, uint64_t nbytes, uint64_t first, uint64_t count, float *iq)
 {
+    e = dev0(e);
     if (!e || !bytes || !iq) return fail(e, SP_E_INVAL, "null argument");
     if (format < 0 || format >= SP_FORMAT_COUNT) return fail(e, SP_E_BAD_FORMAT, "format %d out of range", format);
     if (count == 0) return SP_OK;
@@ -1077,6 +1232,7 @@ extern "C" int sp_decode(sp_engine *e, int format, const void *bytes, uint64_t n
 // ------------------------------------------------------------------ per-launch profiling ring
 extern "C" int sp_profile_enable(sp_engine *e, int slots)
 {
+    e = dev0(e);
     if (!e) return SP_E_INVAL;
     CU(cudaSetDevice(e->dev));
     for (auto ev : e->prof0) cudaEventDestroy(ev);
@@ -1091,6 +1247,7 @@ extern "C" int sp_profile_enable(sp_engine *e, int slots)
 }
 extern "C" int sp_profile_read(sp_engine *e, float *ms, int max)
 {
+    e = dev0(e);
     if (!e || !ms) return SP_E_INVAL;
     CU(cudaSetDevice(e->dev));
     CU(cudaStreamSynchronize(e->stream));
@@ -1108,6 +1265,7 @@ extern "C" int sp_profile_read(sp_engine *e, float *ms, int max)
 // ------------------------------------------------------------------ memory helpers
 extern "C" int sp_device_alloc(sp_engine *e, uint64_t nbytes, void **dptr)
 {
+    e = dev0(e);
     if (!e || !dptr) return SP_E_INVAL;
     CU(cudaSetDevice(e->dev));
     CU(cudaMalloc(dptr, (size_t)((nbytes + 255) & ~255ull) + 256));
@@ -1115,6 +1273,7 @@ extern "C" int sp_device_alloc(sp_engine *e, uint64_t nbytes, void **dptr)
 }
 extern "C" int sp_device_free(sp_engine *e, void *dptr)
 {
+    e = dev0(e);
     if (!e) return SP_E_INVAL;
     CU(cudaSetDevice(e->dev));
     CU(cudaFree(dptr));
@@ -1122,6 +1281,7 @@ extern "C" int sp_device_free(sp_engine *e, void *dptr)
 }
 extern "C" int sp_memcpy_h2d(sp_engine *e, void *dst, const void *src, uint64_t n)
 {
+    e = dev0(e);
     if (!e) return SP_E_INVAL;
     CU(cudaSetDevice(e->dev));
     CU(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, e->stream));
@@ -1130,6 +1290,7 @@ extern "C" int sp_memcpy_h2d(sp_engine *e, void *dst, const void *src, uint64_t 
 }
 extern "C" int sp_memcpy_d2h(sp_engine *e, void *dst, const void *src, uint64_t n)
 {
+    e = dev0(e);
     if (!e) return SP_E_INVAL;
     CU(cudaSetDevice(e->dev));
     CU(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, e->stream));
@@ -1145,6 +1306,10 @@ extern "C" int sp_host_free_pinned(void *hptr) { return cudaFreeHost(hptr) == cu
 extern "C" int sp_device_sync(sp_engine *e)
 {
     if (!e) return SP_E_INVAL;
+    if (!e->subs.empty()) {
+        for (sp_engine *sub : e->subs) { const int rc = sp_device_sync(sub); if (rc) return rc; }
+        return SP_OK;
+    }
     CU(cudaSetDevice(e->dev));
     CU(cudaStreamSynchronize(e->stream));
     return SP_OK;
@@ -1158,6 +1323,7 @@ extern "C" void sp_synth_lut(int16_t *lut)
 
 extern "C" int sp_synth_fill(sp_engine *e, void *dst_dev, int format, uint64_t first, uint64_t count, uint64_t total_samples, uint64_t seed)
 {
+    e = dev0(e);
     if (!e || !dst_dev) return fail(e, SP_E_INVAL, "null argument");
     if (format < 0 || format >= SP_FORMAT_COUNT) return fail(e, SP_E_BAD_FORMAT, "format %d out of range", format);
     CU(cudaSetDevice(e->dev));

@@ -10,11 +10,20 @@
 
 namespace sp {
 
+// cudaFuncSetAttribute is per device: a multi-device engine (sp_create with ndev > 1) launches the same kernel on several
+static inline bool &attr_flag(bool (&flags)[64])
+{
+    int d = 0;
+    cudaGetDevice(&d);
+    return flags[d & 63];
+}
+
 template <int LOG2N, int FMT>
 static cudaError_t launch_one(const Params &p, int grid, size_t smem, cudaStream_t st, int *occ_out)
 {
     auto kfn = render_kernel<LOG2N, FMT>;
-    static bool attr_done = false;           // one engine call at a time (see header)
+    static bool attr_flags[64] = {};         // per device: function attributes belong to the device's context
+    bool &attr_done = attr_flag(attr_flags);
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
@@ -70,7 +79,8 @@ static cudaError_t launch_fast_v(const Params &p, int grid, cudaStream_t st, uns
 {
     using B = FastCfg<FMT, SUB>;
     auto kfn = render_fast_kernel<FMT, SUB>;
-    static bool attr_done = false;
+    static bool attr_flags[64] = {};
+    bool &attr_done = attr_flag(attr_flags);
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::SMEM_BYTES);
         if (e != cudaSuccess) return e;
@@ -96,7 +106,8 @@ static cudaError_t launch_r64_v(const Params &p, int grid, cudaStream_t st, unsi
         return occ_out ? cudaSuccess : cudaErrorInvalidValue;
     } else {
         auto kfn = render_r64_kernel<FMT, SUB>;
-        static bool attr_done = false;
+        static bool attr_flags[64] = {};
+        bool &attr_done = attr_flag(attr_flags);
         if (!attr_done) {
             cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::SMEM_BYTES);
             if (e != cudaSuccess) return e;
@@ -123,7 +134,8 @@ static cudaError_t launch_rc_v(const Params &p, int grid, cudaStream_t st, const
         return occ_out ? cudaSuccess : cudaErrorInvalidValue;
     } else {
         auto kfn = render_rc_kernel<LOG2C, FMT>;
-        static bool attr_done = false;
+        static bool attr_flags[64] = {};
+        bool &attr_done = attr_flag(attr_flags);
         if (!attr_done) {
             cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::SMEM_BYTES);
             if (e != cudaSuccess) return e;

@@ -144,16 +144,20 @@ class PinnedBuffer:
 
 
 class Engine:
-    """One sp_engine == one GPU == one reference worker (sequential requests)."""
+    """One sp_engine == one reference worker (sequential requests).  `device` is one GPU index, or a list of indices for a
+    multi-device engine: `render` of a host-buffer message is then sharded by frame range across those GPUs inside the
+    C ABI (sp_create with ndev > 1) and returns the single-device result."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
         self.lib = load()
         self.h = C.c_void_p()
-        ids = (C.c_int * 1)(int(device))
-        rc = self.lib.sp_create(C.byref(self.h), ids, 1)
+        devs = [int(d) for d in device] if isinstance(device, (list, tuple)) else [int(device)]
+        ids = (C.c_int * len(devs))(*devs)
+        rc = self.lib.sp_create(C.byref(self.h), ids, len(devs))
         if rc:
             raise SpError(rc, (self.lib.sp_last_error(None) or b"").decode())
-        self.device = device
+        self.device = devs[0]
+        self.devices = devs
 
     def close(self):
         if self.h:

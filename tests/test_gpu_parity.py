@@ -536,3 +536,64 @@ def test_randomized_option_sweep(engine, case):
         pytest.skip("shorter than one frame")
     run_both(engine, buf, fmt, n, width, window, gain, rng_db, injective_cmap(cmap_len), chm, wf, want_db=not chm,
              label="random case %d" % i)
+
+
+# ------------------------------------------------------------------ multi-device engine (sp_create with ndev > 1)
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs (run with gpurun --gpus 2)")
+def test_multi_device_engine_equals_single_device(engine):
+    """One C-ABI engine over several GPUs: sp_render shards a whole host-buffer message by frame range (cuts on multiples of
+    8 frames, global positions, halo) and the devices write their bands straight into the caller's image; histograms and
+    min / max are merged like lib/spectroplot.js:1229-1238.  The result must be the single-device result, byte for byte."""
+    import spectro_b200
+    ndev = min(_gpu_count(), 8)
+    multi = spectro_b200.Engine(list(range(ndev)))
+    assert multi.lib.sp_device_count(multi.h) == ndev
+    try:
+        cases = [("CS16", 4096, 1024, 4096, False, False), ("CU8", 1024, 4000, 700, False, False), ("CF32", 512, 960, 512, True, False),
+                 ("CS16", 4096, 200, 3000, False, True), ("CF32", 8192, 64, 8192, False, False), ("CS8", 128, 4003, 100, False, False),
+                 ("CU12", 256, 24, 256, False, False)]
+        for fmt, n, width, hop, wf, chm in cases:
+            S = hop * (width - 1) + n + 5
+            buf = O.synth(fmt, 0, S, S, 0x5EC7C000 + n).tobytes()
+            w, wt = O.window("hann", n)
+            one = engine.render(buf, fmt, n, width, w, 1 / wt, 6, 30, CM256, channel_mode=chm, waterfall=wf)
+            many = multi.render(buf, fmt, n, width, w, 1 / wt, 6, 30, CM256, channel_mode=chm, waterfall=wf)
+            exact = width % 8 == 0
+            for k in ("image", "cB_hist", "c_hist", "gauge_mins", "gauge_maxs", "gauge_amps"):
+                if exact:
+                    assert np.array_equal(one[k], many[k]), (fmt, n, width, k)
+                elif k == "image":                             # odd widths: a frame may change kernels at a cut (ties only)
+                    assert (one[k] != many[k]).any(axis=2).mean() <= 1e-3
+            for k, tol in (("dBfs_min", 0.05), ("dBfs_max", 0.01)):
+                assert one[k] == many[k] or (not exact and abs(one[k] - many[k]) <= tol), (fmt, n, width, k, one[k], many[k])
+            assert int(many["c_hist"].sum()) == n * width
+            if width >= 16 * ndev:
+                assert many["kernel_launches"] > one["kernel_launches"]      # it really ran on several devices
+        # a ragged tail travels with the last shard; errors carry the device's message
+        buf = O.synth("CU8", 0, 40001, 40001, 5).tobytes()[:-1]
+        w, wt = O.window("hann", 256)
+        one = engine.render(buf, "CU8", 256, 800, w, 1 / wt, 6, 30, CM256)
+        many = multi.render(buf, "CU8", 256, 800, w, 1 / wt, 6, 30, CM256)
+        assert np.array_equal(one["image"], many["image"]) and np.array_equal(one["cB_hist"], many["cB_hist"])
+        with pytest.raises(spectro_b200.SpError, match="power of 2"):
+            multi.render(buf, "CU8", 100, 800, w[:100], 1 / wt, 6, 30, CM256)
+        # pinned input: every device streams its own byte range through the pipelined path
+        S = 4096 * 2048
+        pin = spectro_b200.PinnedBuffer(S * 4)
+        pin.array[:] = O.synth("CS16", 0, S, S, 77)
+        w, wt = O.window("blackmanHarris", 4096)
+        one = engine.render(pin.array, "CS16", 4096, 2048, w, 1 / wt, 6, 30, CM256)
+        many = multi.render(pin.array, "CS16", 4096, 2048, w, 1 / wt, 6, 30, CM256)
+        for k in ("image", "cB_hist", "c_hist", "gauge_mins", "gauge_maxs", "gauge_amps"):
+            assert np.array_equal(one[k], many[k]), k
+        pin.free()
+    finally:
+        multi.close()
