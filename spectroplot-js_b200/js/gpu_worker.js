@@ -27,7 +27,9 @@ function formatId(name) {
 
 class GpuWorker {
     constructor(device = 0) {
-        this.engine = addon.create(device) // throws without an sm_100 GPU: there is no CPU fallback
+        // a device index, or an array of indices for one worker that shards each message across several GPUs;
+        // throws without an sm_100 GPU: there is no CPU fallback
+        this.engine = addon.create(device)
         this.onmessage = null
         this.onerror = null
     }

@@ -11,7 +11,7 @@
  *     cc -shared -fPIC -I$(node -p "require('node-addon-api').include_dir || process.execPath+'/../../include/node'") \
  *        -I../../include spectro_napi.c -L../lib -lspectro_b200 -o spectro_napi.node
  *
- * Exports:  create(device) -> external;  destroy(engine);
+ * Exports:  create(device | [devices]) -> external;  destroy(engine);
  *           render(engine, ctx) -> { cB_hist, c_hist, dBfs_min, dBfs_max, gauge_mins, gauge_maxs, gauge_amps, image }
  * where ctx = { buffer:ArrayBuffer, format:int, n, width, block_norm, gain, range, windowc:Float64Array,
  *               cmap:Uint8Array(len*3), channelMode:bool, waterfall:bool }.
@@ -42,11 +42,23 @@ static int get_bool(napi_env env, napi_value obj, const char *key)
 
 static napi_value Create(napi_env env, napi_callback_info info)
 {
-    size_t argc = 1; napi_value argv[1]; int32_t dev = 0;
+    /* create(device) or create([device, device, ...]): several devices make one engine whose render() shards a
+     * message by frame range across them (sp_create with ndev > 1) */
+    size_t argc = 1; napi_value argv[1]; int32_t devs[64] = { 0 }; uint32_t ndev = 1;
     NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
-    if (argc > 0) napi_get_value_int32(env, argv[0], &dev);
+    bool is_array = false;
+    if (argc > 0) napi_is_array(env, argv[0], &is_array);
+    if (is_array) {
+        NAPI_OK(napi_get_array_length(env, argv[0], &ndev));
+        if (ndev < 1 || ndev > 64) { napi_throw_error(env, NULL, "create: 1 .. 64 devices"); return NULL; }
+        for (uint32_t i = 0; i < ndev; i++) {
+            napi_value v;
+            NAPI_OK(napi_get_element(env, argv[0], i, &v));
+            NAPI_OK(napi_get_value_int32(env, v, &devs[i]));
+        }
+    } else if (argc > 0) napi_get_value_int32(env, argv[0], &devs[0]);
     sp_engine *e = NULL;
-    int rc = sp_create(&e, &dev, 1);
+    int rc = sp_create(&e, devs, (int)ndev);
     if (rc) { napi_throw_error(env, NULL, sp_last_error(NULL)); return NULL; }   /* no CPU fallback */
     napi_value ext;
     NAPI_OK(napi_create_external(env, e, NULL, NULL, &ext));

@@ -10,7 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-enum { K_UNDEF, K_NUM, K_BOOL, K_OBJ, K_AB, K_TA, K_EXT, K_FN };
+enum { K_UNDEF, K_NUM, K_BOOL, K_OBJ, K_AB, K_TA, K_EXT, K_FN, K_ARR };
 struct prop { char *key; napi_value val; struct prop *next; };
 struct napi_value__ {
     int kind; double num; int b;
@@ -18,6 +18,7 @@ struct napi_value__ {
     void *data; size_t len;                               /* K_AB: bytes; K_TA: element pointer / element count; K_EXT: pointer */
     napi_typedarray_type tt; napi_value ab; size_t off;   /* K_TA */
     napi_callback cb;                                     /* K_FN */
+    napi_value *items; uint32_t nitems;                   /* K_ARR */
 };
 struct napi_env__ { char err[512]; int pending; struct napi_value__ undef; };
 struct napi_callback_info__ { size_t argc; napi_value *argv; };
@@ -108,6 +109,9 @@ napi_status napi_create_typedarray(napi_env env, napi_typedarray_type type, size
     *r = v;
     return napi_ok;
 }
+napi_status napi_is_array(napi_env env, napi_value v, bool *r) { (void)env; *r = v && v->kind == K_ARR; return napi_ok; }
+napi_status napi_get_array_length(napi_env env, napi_value v, uint32_t *r) { (void)env; if (!v || v->kind != K_ARR) return napi_array_expected; *r = v->nitems; return napi_ok; }
+napi_status napi_get_element(napi_env env, napi_value v, uint32_t i, napi_value *r) { if (!v || v->kind != K_ARR) return napi_array_expected; *r = i < v->nitems ? v->items[i] : &env->undef; return napi_ok; }
 napi_status napi_create_object(napi_env env, napi_value *r) { (void)env; *r = nv(K_OBJ); return napi_ok; }
 napi_status napi_create_double(napi_env env, double d, napi_value *r) { (void)env; napi_value v = nv(K_NUM); v->num = d; *r = v; return napi_ok; }
 napi_status napi_create_function(napi_env env, const char *name, size_t len, napi_callback cb, void *data, napi_value *r)
@@ -125,6 +129,7 @@ napi_value fk_load(napi_env env) { napi_value ex = nv(K_OBJ); return fake_napi_m
 napi_value fk_number(double d) { napi_value v = nv(K_NUM); v->num = d; return v; }
 napi_value fk_bool(int b) { napi_value v = nv(K_BOOL); v->b = b; return v; }
 napi_value fk_object(void) { return nv(K_OBJ); }
+napi_value fk_array(uint32_t n, napi_value *items) { napi_value v = nv(K_ARR); v->items = (napi_value *)malloc(sizeof(napi_value) * (n ? n : 1)); memcpy(v->items, items, sizeof(napi_value) * n); v->nitems = n; return v; }
 napi_value fk_arraybuffer(const void *bytes, size_t n) { napi_value v = nv(K_AB); v->data = malloc(n ? n : 1); memcpy(v->data, bytes, n); v->len = n; return v; }
 napi_value fk_typedarray(int type, napi_value ab, size_t off, size_t length) { napi_value r = NULL; napi_create_typedarray(NULL, (napi_typedarray_type)type, length, ab, off, &r); return r; }
 void fk_set(napi_value o, const char *k, napi_value v) { napi_set_named_property(NULL, o, k, v); }

@@ -49,6 +49,9 @@ napi_status napi_create_arraybuffer(napi_env env, size_t byte_length, void **dat
 napi_status napi_create_typedarray(napi_env env, napi_typedarray_type type, size_t length, napi_value arraybuffer, size_t byte_offset,
                                    napi_value *result);
 napi_status napi_create_object(napi_env env, napi_value *result);
+napi_status napi_is_array(napi_env env, napi_value value, bool *result);
+napi_status napi_get_array_length(napi_env env, napi_value value, uint32_t *result);
+napi_status napi_get_element(napi_env env, napi_value object, uint32_t index, napi_value *result);
 napi_status napi_create_double(napi_env env, double value, napi_value *result);
 napi_status napi_create_function(napi_env env, const char *utf8name, size_t length, napi_callback cb, void *data, napi_value *result);
 

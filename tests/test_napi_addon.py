@@ -30,7 +30,7 @@ def fk():
     lib = C.CDLL(so)
     P = C.c_void_p
     for name, res, args in (("fk_env_new", P, []), ("fk_load", P, [P]), ("fk_number", P, [C.c_double]), ("fk_bool", P, [C.c_int]),
-                            ("fk_object", P, []), ("fk_arraybuffer", P, [P, C.c_size_t]), ("fk_typedarray", P, [C.c_int, P, C.c_size_t, C.c_size_t]),
+                            ("fk_object", P, []), ("fk_array", P, [C.c_uint32, C.POINTER(P)]), ("fk_arraybuffer", P, [P, C.c_size_t]), ("fk_typedarray", P, [C.c_int, P, C.c_size_t, C.c_size_t]),
                             ("fk_set", None, [P, C.c_char_p, P]), ("fk_get", P, [P, P, C.c_char_p]), ("fk_kind", C.c_int, [P]),
                             ("fk_num", C.c_double, [P]), ("fk_data", P, [P]), ("fk_len", C.c_size_t, [P]), ("fk_ta_type", C.c_int, [P]),
                             ("fk_call", P, [P, P, C.c_size_t, C.POINTER(P)]), ("fk_error", C.c_char_p, [P])):
@@ -135,3 +135,13 @@ def test_addon_render_matches_reference_replies(fk):
     with pytest.raises(RuntimeError, match="napi_get_typedarray_info"):
         a.call("render", eng, a.ctx(f, windowc=a.ab(f["windowc"].tobytes())))
     a.call("destroy", eng)
+    # create([devices]): one engine over several GPUs (sp_create with ndev > 1); with one GPU in the box a one-element list
+    import torch
+    ids = list(range(min(torch.cuda.device_count(), 8)))
+    items = (C.c_void_p * len(ids))(*[fk.fk_number(float(i)) for i in ids])
+    multi = a.call("create", fk.fk_array(len(ids), items))
+    f = load("cu8_n256_overlap_w40")
+    r = a.call("render", multi, a.ctx(f))
+    img = a.typed_out(r, "image", U8C, np.uint8)
+    assert (img.reshape(-1, 4) != f["image"].reshape(-1, 4)).any(axis=1).sum() <= 10
+    a.call("destroy", multi)
