@@ -1303,7 +1303,7 @@ class Interp:
         if isinstance(v, str):
             return [str(i) for i in range(len(v))]
         if isinstance(v, JSObject):
-            return [k for k, x in v.props.items() if type(x) is not Getter or True]
+            return list(v.props.keys())
         return []
 
     # ---- compile
@@ -1653,10 +1653,6 @@ class Interp:
                     ex[n] = _lookup(env, n)
             return run_exdecl
         raise SyntaxError("jsmini: cannot compile statement %r" % (k,))
-
-    def c_ref(self, node):
-        """-> (getter(env), setter(env, val)) evaluating sub-expressions once per call of each (used by simple assignment)."""
-        raise NotImplementedError
 
     def c_expr(self, e):
         k = e[0]
@@ -2394,7 +2390,7 @@ def _install_builtins(I):
         "find": native("find", lambda t, a: next((x for i, x in enumerate(list(seq_of(t))) if truthy(I.call(a[0], arg(a, 1), [x, i, t]))), UNDEF)),
         "reduce": native("reduce", a_reduce), "indexOf": native("indexOf", a_index_of),
         "includes": native("includes", lambda t, a: a_index_of(t, a) >= 0),
-        "join": native("join", lambda t, a: (", " if False else (js_to_string(arg(a, 0)) if arg(a, 0) is not UNDEF else ",")).join(
+        "join": native("join", lambda t, a: (js_to_string(arg(a, 0)) if arg(a, 0) is not UNDEF else ",").join(
             "" if (x is UNDEF or x is None) else js_to_string(x) for x in seq_of(t))),
         "concat": native("concat", lambda t, a: JSArray(I, list(t.list) + [y for x in a for y in (x.list if isinstance(x, JSArray) else [x])])),
         "reverse": native("reverse", lambda t, a: (t.list.reverse(), t)[1]),
