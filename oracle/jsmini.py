@@ -2165,8 +2165,8 @@ def _install_builtins(I):
     def js_round(x):
         if x != x or x in (math.inf, -math.inf):
             return x
-        r = math.floor(x + 0.5)
-        return r
+        r = math.floor(x)                 # nearest integer, ties toward +Infinity; x - floor(x) is exact
+        return r + 1 if x - r >= 0.5 else r
 
     def js_minmax(is_max):
         def g(this, a):
