@@ -155,3 +155,29 @@ def test_file_to_pyramid_on_the_gpu(engine, tmp_path):
     levels = egress.write_pyramid(str(tmp_path / "pyr"), engine, buf, "CF32", 2048, 24, (1, 2, 4), np.array(wb["window"]), 1 / wb["weight"], 6, 30, cm, 64)
     assert [l["meta"]["width"] for l in levels] == [24, 48, 96] and all(sum(l["meta"]["c_hist"]) == 2048 * l["meta"]["width"] for l in levels)
     assert len(levels[2]["tiles"]) == 2
+
+
+@pytest.mark.gpu
+def test_command_line_file_to_png(engine, tmp_path):
+    """python -m spectro_b200 capture -> PNG + JSON: name parsing, option parsers, render, egress in one go."""
+    import subprocess, sys
+    from spectro_b200 import egress, windows, cmaps
+    S = 200000
+    raw = O.synth("CU8", 0, S, S, 21).tobytes()
+    cap = tmp_path / "g005_433.92M_250k.cu8"
+    cap.write_bytes(raw)
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", "spectroplot-js_b200"))
+    out = subprocess.run([sys.executable, "-m", "spectro_b200", str(cap), "--fftN", "1024", "--windowF", "hann", "--cmap", "viridis",
+                          "--width", "800", "--out", str(tmp_path / "pic")], cwd=root, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    info = json.loads(out.stdout.strip().splitlines()[-1])
+    assert info["format"] == "CU8" and info["center_freq"] == 433920000.0 and info["sample_rate"] == 250000.0
+    assert info["width"] == 800 and info["height"] == 1024
+    img = egress.read_png_rgba(open(tmp_path / "pic.png", "rb").read())
+    w = windows.hannWindow(1024)
+    cm = [list(c) for c in cmaps.cmaps["viridis_cmap"]]
+    cm[0] = [0, 0, 0]; cm[-1] = [255, 255, 255]
+    ora = O.render(raw, "CU8", 1024, 800, np.array(w["window"]), 1 / w["weight"], 6, 30, cmaps.cmap_bytes(cm))
+    assert img.shape == ora.image.shape and (img != ora.image).any(axis=2).mean() <= 1e-3
+    meta = json.load(open(tmp_path / "pic.json"))
+    assert sum(meta["c_hist"]) == 800 * 1024
