@@ -315,6 +315,19 @@ __device__ __forceinline__ cf cmul(cf a, float2 w)
 __device__ __forceinline__ cf mul_mj(cf a) { const float2 f = cun(a); return cpk(f.y, -f.x); }
 __device__ __forceinline__ cf mul_pj(cf a) { const float2 f = cun(a); return cpk(-f.y, f.x); }
 
+// decode_raw() as a packed complex value.  CS16: both halves take the same constant, so the two subtractions are one FADD2
+// (one issue slot per sample less in the fused kernels' load phase; every step is exact as in decode_raw).
+template <int FMT> __device__ __forceinline__ cf decode_raw_cf(const uint8_t *__restrict__ buf, long long s, int rt_fmt)
+{
+    if constexpr (FMT == CS16) {
+        const unsigned v = *reinterpret_cast<const unsigned *>(buf + 4 * s) ^ 0x80008000u;
+        const cf u = cpk(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7610)), __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7632)));
+        return cadd(u, cpk(-8421376.0f, -8421376.0f));
+    } else {
+        return cpk(decode_raw<FMT>(buf, s, rt_fmt));
+    }
+}
+
 #define SP_SQRT1_2 0.70710678118654752440f
 #define SP_COS_PI_8 0.92387953251128675613f
 #define SP_SIN_PI_8 0.38268343236508977173f

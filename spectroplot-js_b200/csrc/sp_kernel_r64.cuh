@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
             } else {
                 const unsigned char *rp = raw + s_off[s * 2 + fpar];
 #pragma unroll
-                for (int a = 0; a < 64; a++) v[a] = cpk(decode_raw<FMT>(rp, T * a + t, p.format));
+                for (int a = 0; a < 64; a++) v[a] = decode_raw_cf<FMT>(rp, T * a + t, p.format);
                 // raw sample at p0 + n/2 (lib/worker.js:131-133); the power-of-two scale is exact
                 if (t == 0 && valid) p.fmid[p.chunk_first + xr0 + fl] = make_float2(cre(v[32]) * raw_scale<FMT>(), cim(v[32]) * raw_scale<FMT>());
                 const float4 *wrow = reinterpret_cast<const float4 *>(s_win + t * B::WIN_PITCH);

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(384, 1) render_rc_kernel(const Params p, const
             {
                 const unsigned char *rp = xs + fi * B::RAWP + s_off[(s * 2 + fpar) * FS + fi];
 #pragma unroll
-                for (int a = 0; a < 64; a++) v[a] = cpk(decode_raw<FMT>(rp, C * a + t, p.format));
+                for (int a = 0; a < 64; a++) v[a] = decode_raw_cf<FMT>(rp, C * a + t, p.format);
                 // raw sample at p0 + n/2 (lib/worker.js:131-133); the power-of-two scale is exact
                 if (t == 0 && valid) p.fmid[p.chunk_first + xr0 + fl] = make_float2(cre(v[32]) * raw_scale<FMT>(), cim(v[32]) * raw_scale<FMT>());
                 const float4 *wrow = reinterpret_cast<const float4 *>(s_win + t * 64);
