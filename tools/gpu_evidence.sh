@@ -9,4 +9,4 @@ timeout 600 ncu --metrics $M --clock-control none -k regex:render_r64 --csv --lo
 for tool in memcheck racecheck synccheck; do
   timeout 900 compute-sanitizer --tool $tool python tools/san_multi.py > $OUT/san_${tool}_$TAG.log 2>&1; echo "rc=$?" >> $OUT/san_${tool}_$TAG.log
 done
-tail -4 $OUT/san_*_$TAG.log; wc -l $OUT/overlap_$TAG.csv
+for f in $OUT/san_*_$TAG.log; do tail -n 3 $f; done; wc -l $OUT/overlap_$TAG.csv
