@@ -409,13 +409,13 @@ extern "C" const char *sp_kernel_plan(sp_engine *e, int format, int n, int chann
              specialised(format) ? k_names[format] : "runtime-format", pl.tile, pl.smem_x * 8, channel_mode ? " +splitreal" : "");
     if (pl.log2k >= 8 && pl.log2k <= 11 && !channel_mode && !getenv("SP_NO_FAST") && use_r64() && rc_for(format) && sp::sample_width(format) <= 8) {
         const size_t l = strlen(buf);
-        snprintf(buf + l, sizeof buf - l, " | spectrogram fast path: render_rc_kernel<N=64x%d, tile=%d frames> (one exchange, joint histogram, TMA-staged input)",
+        snprintf(buf + l, sizeof buf - l, " | fast path (spectrogram and waterfall): render_rc_kernel<N=64x%d, tile=%d frames> (one exchange, joint histogram, TMA-staged input)",
                  (1 << pl.log2k) / 64, 65536 >> pl.log2k);
     }
     if (pl.log2k == 12 && !channel_mode && !getenv("SP_NO_FAST")) {
         const size_t l = strlen(buf);
         if (use_r64() && (pl.sub_r > 1 ? sp_r64_cf32 != nullptr : r64_for(format) != nullptr) && (pl.sub_r > 1 || sp::sample_width(format) <= 8))
-            snprintf(buf + l, sizeof buf - l, " | spectrogram fast path: render_r64_kernel<streams=4,tile=16 frames> (64x64 FFT, one exchange, joint histogram, TMA-staged input)");
+            snprintf(buf + l, sizeof buf - l, " | fast path (spectrogram and waterfall): render_r64_kernel<streams=4,tile=16 frames> (64x64 FFT, one exchange, joint histogram, TMA-staged input)");
         else
             snprintf(buf + l, sizeof buf - l, " | spectrogram fast path: render_fast_kernel<slots=2,frames=8> (TMA-staged input, packed fp32)");
     }
@@ -629,10 +629,10 @@ static bool fast_eligible(const Params &p)
 }
 // render_r64_kernel / render_rc_kernel: any width (rows that are not 32-byte aligned are written word by word), so the
 // same frames take the same kernel whether a message is rendered in one piece, in pipeline chunks or in shards
-static bool fused_eligible(const Params &p)
+static bool fused_eligible(const Params &p, bool waterfall_ok = false)
 {
     static const bool off = getenv("SP_NO_FAST") != nullptr;
-    return !off && p.image && !p.waterfall && !p.channel_mode && !p.db_out && p.cmap_len <= 256 && (p.chunk_first % 8 == 0) &&
+    return !off && p.image && (!p.waterfall || waterfall_ok) && !p.channel_mode && !p.db_out && p.cmap_len <= 256 && (p.chunk_first % 8 == 0) &&
            (((uintptr_t)p.image) & 3) == 0;
 }
 // Frames [0, *nfast) of the chunk described by q go through the fast kernel: whole tiles of 8 frames that
@@ -768,14 +768,14 @@ static int enqueue_frames(sp_engine *e, Job &j, Params &p)
     int occ = 0;
     if (j.plan.sub_r == 1) {
         Params q = p;
-        if (j.plan.log2k == 12 && fused_eligible(p) && use_r64() && r64_for(fmt)) {
+        if (j.plan.log2k == 12 && fused_eligible(p, /* waterfall rows in the store warps */ true) && use_r64() && r64_for(fmt)) {
             long long nfast = 0;
             int rc = launch_r64_kernel(e, r64_for(fmt), q, &nfast);
             if (rc) return rc;
             q.chunk_first += nfast;
             q.chunk_frames -= nfast;
         }
-        if (j.plan.log2k >= 8 && j.plan.log2k <= 11 && fused_eligible(p) && use_r64() && rc_for(fmt)) {
+        if (j.plan.log2k >= 8 && j.plan.log2k <= 11 && fused_eligible(p, true) && use_r64() && rc_for(fmt)) {
             long long nfast = 0;
             int rc = launch_rc_kernel(e, rc_for(fmt), j.plan.log2k, q, &nfast);
             if (rc) return rc;

@@ -154,8 +154,28 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
                 mbar_wait(s_full + h, kk & 1);
                 const size_t x0 = (size_t)(p.chunk_first + xr0) + 8 * h;
                 const bool live = xr0 + 8 * h < p.chunk_frames;        // partial last tile: chunk_frames is a multiple of 8
+                if constexpr (!SUB) {
+                    if (p.waterfall && live) {
+                        // waterfall layout (lib/worker.js:116): frame x is image row nframes - 1 - x, bin b is column
+                        // n - 1 - y = (b + n/2 - 1) mod n.  A staged word holds bins k0 + 64*(4m + j): for a fixed (m, j) the
+                        // lanes' bins - and columns - are consecutive, so every store instruction writes 128 contiguous bytes.
 #pragma unroll 1
-                for (int i = 0; i < (live ? 8 : 0); i++) {
+                        for (int f = 0; f < 8; f++) {
+                            uint32_t *rowp = reinterpret_cast<uint32_t *>(p.image) + (size_t)N * (size_t)(p.nframes - 1 - (long long)(x0 + f));
+                            const unsigned *src = s_stage + (8 * h + f) * B::ST_PITCH + ht;
+#pragma unroll
+                            for (int i = 0; i < 8; i++) {
+                                const int id = ht + B::STORE_THREADS * i, k0 = id & 63, m = id >> 6;
+                                const unsigned w = src[B::STORE_THREADS * i];
+#pragma unroll
+                                for (int j = 0; j < 4; j++)
+                                    rowp[(k0 + 64 * (4 * m + j) + N / 2 - 1) & (N - 1)] = lut_at(lut_base, w, j);
+                            }
+                        }
+                    }
+                }
+#pragma unroll 1
+                for (int i = 0; i < ((live && (SUB || !p.waterfall)) ? 8 : 0); i++) {
                     // bins k0 + 64*(4m + j), j = 0..3, of the half's 8 frames: one 32-byte sector per row
                     const int id = ht + B::STORE_THREADS * i, k0 = id & 63, m = id >> 6;
                     const unsigned *src = s_stage + (8 * h) * B::ST_PITCH + m * 64 + k0;

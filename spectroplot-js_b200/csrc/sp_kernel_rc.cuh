@@ -151,8 +151,24 @@ __global__ void __launch_bounds__(384, 1) render_rc_kernel(const Params p, const
                 mbar_wait(s_full + h, kk & 1);
                 const size_t x0 = (size_t)(p.chunk_first + xr0) + HF * h;
                 const unsigned *half = s_stage + h * B::HALF_WORDS;
+                if (p.waterfall) {
+                    // waterfall layout (lib/worker.js:116): frame x is image row nframes - 1 - x, bin b is column (b + n/2 - 1) mod n.
+                    // Item = (frame, m, o): o = tc*RPT + r runs over 64 consecutive bins, so the lanes of a store write
+                    // consecutive columns (128 contiguous bytes); the staged word of (m, o) sits at m*64 + r*C + tc.
+                    constexpr int MG = C / 4 > 0 ? C / 4 : 1;           // 64-bin groups per staged byte position
 #pragma unroll 1
-                for (int i = 0; i < (HF / 8) * (N / 4) / B::STORE_THREADS; i++) {
+                    for (int i = 0; i < HF * MG * 64 / B::STORE_THREADS; i++) {
+                        const int id = ht + B::STORE_THREADS * i, o = id & 63, rest = id >> 6;
+                        const int m = rest % MG, fl = rest / MG;
+                        if (xr0 + HF * h + fl >= p.chunk_frames) continue;               // partial last tile
+                        const unsigned w = half[fl * B::FPW + m * 64 + (o % RPT) * C + o / RPT];
+                        uint32_t *rowp = reinterpret_cast<uint32_t *>(p.image) + (size_t)N * (size_t)(p.nframes - 1 - (long long)(x0 + fl));
+#pragma unroll
+                        for (int j = 0; j < 4; j++) rowp[(o + 64 * (4 * m + j) + N / 2 - 1) & (N - 1)] = lut_at(lut_base, w, j);
+                    }
+                }
+#pragma unroll 1
+                for (int i = 0; i < (p.waterfall ? 0 : (HF / 8) * (N / 4) / B::STORE_THREADS); i++) {
                     // item = (8-frame group g, word w): word w = m*64 + r*C + tc holds bins (tc*RPT + r) + 64*(4m + j), j = 0..3
                     const int id = ht + B::STORE_THREADS * i;
                     const int g = id % B::G, rest = id / B::G;

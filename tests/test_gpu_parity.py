@@ -597,3 +597,19 @@ def test_multi_device_engine_equals_single_device(engine):
         pin.free()
     finally:
         multi.close()
+
+
+@pytest.mark.parametrize("fmt,n,width", [("CS16", 4096, 40), ("CS16", 4096, 21), ("CF32", 4096, 64), ("CU8", 1024, 200), ("CS16", 2048, 37),
+                                         ("CF32", 512, 136), ("CS4", 256, 300)])
+def test_waterfall_on_the_fused_kernels(engine, fmt, n, width):
+    """turnFlip / waterfall (lib/worker.js:116) through render_r64_kernel / render_rc_kernel: frame x is image row W - 1 - x,
+    bin b is column (b + n/2 - 1) mod n; full and partial tiles, plus the same message through the pipelined host path."""
+    S = n * (width // 2 + 3) + 11
+    buf = O.synth(fmt, 0, S, S, 0x5EC7D000 + n + width).tobytes()
+    gpu, ora, nbad = run_both(engine, buf, fmt, n, width, "hann", waterfall=True, want_db=False)
+    assert gpu["image"].shape == (width, n, 4)
+    plain = engine.render(buf, fmt, n, width, *O.window("hann", n)[:1], 1 / O.window("hann", n)[1], 6, 30, CM256)
+    # the waterfall picture is the spectrogram transposed and flipped both ways
+    assert np.array_equal(gpu["image"], plain["image"].transpose(1, 0, 2)[::-1, ::-1])
+    for k in ("cB_hist", "c_hist", "gauge_mins", "gauge_maxs", "gauge_amps"):
+        assert np.array_equal(gpu[k], plain[k]), k
