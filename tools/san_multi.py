@@ -17,7 +17,10 @@ cases = [("CS16", 4096, 32, False, False),      # render_r64_kernel, full tiles
          ("CU12", 512, 24, False, True),        # split-real
          ("CS8", 2048, 13, True, False),        # waterfall layout
          ("CF32", 8192, 16, False, False),      # four-step: prepass_kernel + r64 SUB
-         ("CS16", 16384, 9, False, True)]       # four-step + spectrum epilogue
+         ("CS16", 16384, 9, False, True),       # four-step + spectrum epilogue
+         ("CS16", 4096, 40, True, False),       # waterfall rows from the r64 store warps (full + partial tile)
+         ("CU8", 1024, 72, True, False),        # waterfall rows from the rc store warps
+         ("CF32", 256, 300, True, False)]       # rc C = 4, waterfall
 only = [int(a) for a in sys.argv[1:]]
 for i, (fmt, n, width, wf, chm) in enumerate(cases):
     if only and i not in only:
