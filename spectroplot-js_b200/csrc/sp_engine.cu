@@ -629,10 +629,10 @@ static bool fast_eligible(const Params &p)
 }
 // render_r64_kernel / render_rc_kernel: any width (rows that are not 32-byte aligned are written word by word), so the
 // same frames take the same kernel whether a message is rendered in one piece, in pipeline chunks or in shards
-static bool fused_eligible(const Params &p, bool waterfall_ok = false)
+static bool fused_eligible(const Params &p, bool waterfall_ok = false, bool split_ok = false)
 {
     static const bool off = getenv("SP_NO_FAST") != nullptr;
-    return !off && p.image && (!p.waterfall || waterfall_ok) && !p.channel_mode && !p.db_out && p.cmap_len <= 256 && (p.chunk_first % 8 == 0) &&
+    return !off && p.image && (!p.waterfall || waterfall_ok) && (!p.channel_mode || split_ok) && !p.db_out && p.cmap_len <= 256 && (p.chunk_first % 8 == 0) &&
            (((uintptr_t)p.image) & 3) == 0;
 }
 // Frames [0, *nfast) of the chunk described by q go through the fast kernel: whole tiles of 8 frames that
@@ -768,7 +768,7 @@ static int enqueue_frames(sp_engine *e, Job &j, Params &p)
     int occ = 0;
     if (j.plan.sub_r == 1) {
         Params q = p;
-        if (j.plan.log2k == 12 && fused_eligible(p, /* waterfall rows in the store warps */ true) && use_r64() && r64_for(fmt)) {
+        if (j.plan.log2k == 12 && fused_eligible(p, /* waterfall rows in the store warps */ true, /* split-real in the FFT warps */ true) && use_r64() && r64_for(fmt)) {
             long long nfast = 0;
             int rc = launch_r64_kernel(e, r64_for(fmt), q, &nfast);
             if (rc) return rc;

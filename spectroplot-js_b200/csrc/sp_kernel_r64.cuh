@@ -31,7 +31,7 @@ namespace sp {
 template <int FMT, bool SUB> struct R64Cfg {
     static constexpr int N = 4096, T = 64, STREAMS = 4, FFT_THREADS = T * STREAMS, STORE_THREADS = 128, THREADS = FFT_THREADS + STORE_THREADS;
     static constexpr int STEPS = 4, F = STREAMS * STEPS;                         // 16 frames per tile
-    static constexpr int FFT_REGS = 232, STORE_REGS = 40;                        // 256 * 232 + 128 * 40 <= 65536
+    static constexpr int FFT_REGS = 232, STORE_REGS = 40;                        // 256 * 232 + 128 * 40 == 384 * 168, the CTA's allocation at launch: setmaxnreg only moves registers inside it
     static constexpr int SWB = SUB ? 8 : sample_width(FMT == FMT_RUNTIME ? CF64 : FMT);
     static constexpr bool OK = SUB || ((FMT != FMT_RUNTIME) && SWB <= 8);       // raw frame fits the exchange buffer
     static constexpr int XP = 66;                                                // exchange row pitch (float2): LDS.128 conflict-free
@@ -295,13 +295,65 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
                 }
             }
             stream_barrier(s);                                          // the exchange buffer is free: prefetch the stream's next frame
-            if (t == 0) {
+            const bool split = !SUB && p.channel_mode;                  // split-real needs the buffer once more, see below
+            auto prefetch = [&]() {
                 if (step < B::STEPS - 1) stage(xr0 + fl + B::STREAMS, k0sub, fpar);
                 else if (next_tile < p.ntiles) stage(tile_xr0(next_tile) + s, SUB ? (int)(next_tile % sub_r) : 0, fpar);
-            }
+            };
+            if (t == 0 && !split) prefetch();
             // first frame of this stream in staging half step/2: the store warps must be done with the half (previous tile)
             if ((step & 1) == 0) mbar_wait(s_empty + half, (kk + 1) & 1);
             dft<64>(v);                                                 // v[k1] is bin t + 64*k1
+            if constexpr (!SUB) {
+                if (split) {
+                    // ---------------- split-real post-process (lib/fft_nayuki.js:103-119) ----------------
+                    // bin i = t + 64*k1 pairs with bin n - i = (64 - t) + 64*(63 - k1): thread 64 - t, register 63 - k1 (thread 0
+                    // pairs with itself, register 64 - k1).  One more pass through the exchange buffer: rows written with
+                    // STS.128, the partner's row read back reversed with LDS.128 (both conflict-free at this pitch).
+                    auto split_lo = [](cf a, cf b) {                    // i < n/2:  (re_i + re_p, im_i - im_p) / 2
+                        const float2 fb = cun(b);
+                        return cscale(cadd(a, cpk(fb.x, -fb.y)), 0.5f);
+                    };
+                    auto split_hi = [](cf a, cf b) {                    // i > n/2:  (im_p + im_i, -re_p + re_i) / 2, p = n - i
+                        const float2 fa = cun(a), fb = cun(b);
+                        return cscale(cadd(cpk(fa.y, fa.x), cpk(fb.y, -fb.x)), 0.5f);
+                    };
+                    {
+                        float4 *wrow = reinterpret_cast<float4 *>(X + t * B::XP);
+#pragma unroll
+                        for (int m = 0; m < 32; m++) {
+                            const float2 a = cun(v[2 * m]), b = cun(v[2 * m + 1]);
+                            wrow[m] = make_float4(a.x, a.y, b.x, b.y);
+                        }
+                    }
+                    stream_barrier(s);
+                    if (t == 0) {
+#pragma unroll
+                        for (int k1 = 1; k1 < 32; k1++) {
+                            const cf a = v[k1], b = v[64 - k1];
+                            v[k1] = split_lo(a, b);
+                            v[64 - k1] = split_hi(b, a);
+                        }
+                        v[0] = cpk(cre(v[0]), 0.0f);                    // imag[0] = 0
+                        v[32] = cpk(0.0f, 0.0f);                        // real[n/2] = imag[0] (just zeroed), imag[n/2] = 0
+                    } else {
+                        const float4 *prow = reinterpret_cast<const float4 *>(X + (64 - t) * B::XP);
+#pragma unroll
+                        for (int a = 0; a < 32; a++) {
+                            const float4 q = prow[31 - a];              // partner registers 62 - 2a (.xy) and 63 - 2a (.zw)
+                            if (a < 16) {
+                                v[2 * a] = split_lo(v[2 * a], cpk(q.z, q.w));
+                                v[2 * a + 1] = split_lo(v[2 * a + 1], cpk(q.x, q.y));
+                            } else {
+                                v[2 * a] = split_hi(v[2 * a], cpk(q.z, q.w));
+                                v[2 * a + 1] = split_hi(v[2 * a + 1], cpk(q.x, q.y));
+                            }
+                        }
+                    }
+                    stream_barrier(s);                                  // now the buffer is free
+                    if (t == 0) prefetch();
+                }
+            }
 
             // ---------------- per-bin epilogue (lib/worker.js:85-122) ----------------
             float amin = __int_as_float(0x7f800000), amax = 0.0f, prev = 0.0f;

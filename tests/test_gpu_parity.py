@@ -613,3 +613,17 @@ def test_waterfall_on_the_fused_kernels(engine, fmt, n, width):
     assert np.array_equal(gpu["image"], plain["image"].transpose(1, 0, 2)[::-1, ::-1])
     for k in ("cB_hist", "c_hist", "gauge_mins", "gauge_maxs", "gauge_amps"):
         assert np.array_equal(gpu[k], plain[k]), k
+
+
+@pytest.mark.parametrize("fmt,width,wf", [("CS16", 40, False), ("CF32", 21, False), ("CS16", 24, True), ("CU8", 64, False)])
+def test_split_real_on_the_fused_kernel(engine, fmt, width, wf):
+    """channelMode (two real channels, lib/fft_nayuki.js:103-119) inside render_r64_kernel: bin i pairs with bin n - i held by
+    thread 64 - t, exchanged through the stream's buffer; bins 0 and n/2 follow the reference (imag[0] = 0, both parts of n/2 = 0)."""
+    n = 4096
+    S = n * (width // 2 + 3) + 17
+    buf = O.synth(fmt, 0, S, S, 0x5EC7E000 + width).tobytes()
+    gpu, ora, nbad = run_both(engine, buf, fmt, n, width, "hann", channel_mode=True, waterfall=wf, want_db=False)
+    assert "render_r64_kernel" in engine.kernel_plan(fmt, n)
+    # the n/2 row is -inf (|X|^2 == 0): colour 0 and dB bin 0 (~~(+Infinity) == 0), like the reference
+    g = gray_from_image(gpu["image"], CM256, n, width, wf)
+    assert (g[:, n // 2] == 0).all() and gpu["dBfs_min"] == -np.inf
