@@ -97,6 +97,27 @@ static cudaError_t launch_fast_v(const Params &p, int grid, cudaStream_t st, uns
 }
 
 // N = 4096 "64 x 64" path: one CTA of 4 x 64 threads per SM, 16 frames per tile (sp_kernel_r64.cuh).
+template <int FMT, bool SUB, bool OPT>
+static cudaError_t launch_r64_k(const Params &p, int grid, cudaStream_t st, unsigned *tile_counter, const float2 *tw14, int *occ_out)
+{
+    using B = R64Cfg<FMT, SUB>;
+    auto kfn = render_r64_kernel<FMT, SUB, OPT>;
+    static bool attr_flags[64] = {};
+    bool &attr_done = attr_flag(attr_flags);
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    if (occ_out) {
+        int nb = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, B::THREADS, B::SMEM_BYTES);
+        *occ_out = nb;
+        return e;
+    }
+    kfn<<<grid, B::THREADS, B::SMEM_BYTES, st>>>(p, tw14, tile_counter);
+    return cudaGetLastError();
+}
 template <int FMT, bool SUB>
 static cudaError_t launch_r64_v(const Params &p, int grid, cudaStream_t st, unsigned *tile_counter, const float2 *tw14, int *occ_out)
 {
@@ -104,23 +125,12 @@ static cudaError_t launch_r64_v(const Params &p, int grid, cudaStream_t st, unsi
     if constexpr (!B::OK) {
         if (occ_out) *occ_out = 0;
         return occ_out ? cudaSuccess : cudaErrorInvalidValue;
+    } else if constexpr (SUB) {
+        return launch_r64_k<FMT, true, false>(p, grid, st, tile_counter, tw14, occ_out);
     } else {
-        auto kfn = render_r64_kernel<FMT, SUB>;
-        static bool attr_flags[64] = {};
-        bool &attr_done = attr_flag(attr_flags);
-        if (!attr_done) {
-            cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::SMEM_BYTES);
-            if (e != cudaSuccess) return e;
-            attr_done = true;
-        }
-        if (occ_out) {
-            int nb = 0;
-            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, B::THREADS, B::SMEM_BYTES);
-            *occ_out = nb;
-            return e;
-        }
-        kfn<<<grid, B::THREADS, B::SMEM_BYTES, st>>>(p, tw14, tile_counter);
-        return cudaGetLastError();
+        // messages that ask for the waterfall layout or the split-real post-process take the kernel compiled with them
+        if (p.waterfall || p.channel_mode) return launch_r64_k<FMT, false, true>(p, grid, st, tile_counter, tw14, occ_out);
+        return launch_r64_k<FMT, false, false>(p, grid, st, tile_counter, tw14, occ_out);
     }
 }
 

@@ -69,7 +69,10 @@ __device__ __forceinline__ void stream_barrier(int stream)
 }
 
 // tw14: [64][14] float2 = W_4096^{t*k}, k = 1..7, 8, 16, 24, 32, 40, 48, 56
-template <int FMT, bool SUB>
+// OPT = false: the plain spectrogram kernel (the headline path, nothing else compiled in); OPT = true: the same kernel with
+// the waterfall rows and the split-real post-process compiled in (selected by the launcher when a message asks for them),
+// so that the options cost the plain kernel neither registers nor instruction-cache footprint.
+template <int FMT, bool SUB, bool OPT = false>
 __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, const float2 *__restrict__ tw14,
                                                             unsigned *__restrict__ tile_counter)
 {
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
                 mbar_wait(s_full + h, kk & 1);
                 const size_t x0 = (size_t)(p.chunk_first + xr0) + 8 * h;
                 const bool live = xr0 + 8 * h < p.chunk_frames;        // partial last tile: chunk_frames is a multiple of 8
-                if constexpr (!SUB) {
+                if constexpr (OPT && !SUB) {
                     if (p.waterfall && live) {
                         // waterfall layout (lib/worker.js:116): frame x is image row nframes - 1 - x, bin b is column
                         // n - 1 - y = (b + n/2 - 1) mod n.  A staged word holds bins k0 + 64*(4m + j): for a fixed (m, j) the
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
                     }
                 }
 #pragma unroll 1
-                for (int i = 0; i < ((live && (SUB || !p.waterfall)) ? 8 : 0); i++) {
+                for (int i = 0; i < ((live && (!OPT || SUB || !p.waterfall)) ? 8 : 0); i++) {
                     // bins k0 + 64*(4m + j), j = 0..3, of the half's 8 frames: one 32-byte sector per row
                     const int id = ht + B::STORE_THREADS * i, k0 = id & 63, m = id >> 6;
                     const unsigned *src = s_stage + (8 * h) * B::ST_PITCH + m * 64 + k0;
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
                 }
             }
             stream_barrier(s);                                          // the exchange buffer is free: prefetch the stream's next frame
-            const bool split = !SUB && p.channel_mode;                  // split-real needs the buffer once more, see below
+            const bool split = OPT && !SUB && p.channel_mode;           // split-real needs the buffer once more, see below
             auto prefetch = [&]() {
                 if (step < B::STEPS - 1) stage(xr0 + fl + B::STREAMS, k0sub, fpar);
                 else if (next_tile < p.ntiles) stage(tile_xr0(next_tile) + s, SUB ? (int)(next_tile % sub_r) : 0, fpar);
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
             // first frame of this stream in staging half step/2: the store warps must be done with the half (previous tile)
             if ((step & 1) == 0) mbar_wait(s_empty + half, (kk + 1) & 1);
             dft<64>(v);                                                 // v[k1] is bin t + 64*k1
-            if constexpr (!SUB) {
+            if constexpr (OPT && !SUB) {
                 if (split) {
                     // ---------------- split-real post-process (lib/fft_nayuki.js:103-119) ----------------
                     // bin i = t + 64*k1 pairs with bin n - i = (64 - t) + 64*(63 - k1): thread 64 - t, register 63 - k1 (thread 0
