@@ -1,5 +1,7 @@
+"""Throughput of the reference options other than the plain spectrogram (waterfall / turnFlip, split-real / channelMode) against
+the plain render, device resident.  usage (under gpurun): python tools/mode_bench.py"""
 import sys, os, json
-ROOT="/root/repo"
+ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "spectroplot-js_b200")): sys.path.insert(0, p)
 import numpy as np, torch, spectro_b200
 from spectro_b200 import windows, cmaps
