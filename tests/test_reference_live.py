@@ -83,3 +83,59 @@ def test_sampleview_decode_and_slice_random(js):
             for i in range(k):
                 b = js.call(js.get_prop(sv, "slice"), sv, [i, k, 0, end])
                 assert bytes(py.slice(i, k, 0, end)) == bytes(b.data), (fmt, i, k)
+
+
+def test_worker_random_messages_equal_the_oracle():
+    """Seeded random worker messages (format, N <= 256, width, hop, window, gain, range, colormap length, channel mode,
+    waterfall, ragged tails, occasional NaN / silence) through the reference's unmodified lib/worker.js and through the C
+    oracle: every reply field must be identical."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    from make_ref_golden import RefWorker, hist_to_np, injective_cmap
+    from oracle import oracle as O
+    from spectro_b200.samples import SampleView
+    W = RefWorker()
+    I = W.I
+    rnd = random.Random(424242)
+    fmts = list(O.FORMATS)
+    wins = ["rectangular", "bartlett", "hamming", "hann", "blackman", "blackmanHarris"]
+    checked = 0
+    for case in range(70):
+        fmt = rnd.choice(fmts)
+        n = 1 << rnd.randint(3, 8)
+        width = rnd.choice([2, 3, 5, 8, 13, 24, 33])
+        hop = rnd.choice([0.0, 0.4, 1.0, 1.0, 2.3])
+        S = n + int(hop * n * (width - 1)) + rnd.randint(0, 9)
+        buf = bytearray(O.synth(fmt, 0, S, S, 1000 + case).tobytes())
+        sv = SampleView(fmt)
+        if rnd.random() < 0.2 and sv.sampleWidth > sv.elementSize:
+            del buf[-sv.elementSize:]                                  # ragged tail (fractional sampleCount)
+        if fmt == "CF32" and rnd.random() < 0.3:
+            a = np.frombuffer(bytes(buf), "<f4").copy(); a[rnd.randrange(len(a))] = np.nan; buf = bytearray(a.tobytes())
+        if rnd.random() < 0.1:
+            buf = bytearray(len(buf))                                  # silence: log10(0)
+        if len(buf) / sv.sampleWidth < n:
+            continue
+        window = rnd.choice(wins)
+        gain, rng = rnd.choice([-10, 0, 6, 25]), rnd.choice([6, 30, 90, -30])
+        cm = injective_cmap(rnd.choice([2, 64, 256, 300]))
+        chm, wf = rnd.random() < 0.25, rnd.random() < 0.25
+        windowc, weight = W.window(window, n)
+        jcm = W.cmap(cm)
+        r = W.post(dict(block_norm=1.0 / weight, gain=gain, range=rng, cmap=jcm, n=n, windowc=windowc, width=width, offset=case,
+                        buffer=I.from_py(bytes(buf)), format=fmt, channelMode=chm, waterfall=wf))
+        g = lambda k: I.get_prop(r, k)
+        cmb = np.array(I.to_py(jcm), np.uint8)
+        o = O.render(bytes(buf), fmt, n, width, np.array(I.to_py(windowc), np.float64), 1.0 / weight, gain, rng, cmb, chm, wf)
+        label = (case, fmt, n, width, window, gain, rng, len(cm), chm, wf)
+        assert np.array_equal(I.get_prop(g("imageData"), "data").arr, o.image.reshape(-1)), label
+        assert np.array_equal(hist_to_np(I, g("cB_hist"))[0], o.cB_hist.astype(np.float64)), label
+        assert np.array_equal(hist_to_np(I, g("c_hist"))[0], o.c_hist.astype(np.float64)), label
+        for k in ("gauge_mins", "gauge_maxs", "gauge_amps"):
+            assert np.array_equal(g(k).arr, getattr(o, k)), label + (k,)
+        for k in ("dBfs_min", "dBfs_max"):
+            a, b = float(g(k)), float(getattr(o, k))
+            assert a == b or (a != a and b != b), label + (k, a, b)
+        assert g("offset") == case
+        checked += 1
+    assert checked >= 60
