@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
                             v[k1] = split_lo(a, b);
                             v[64 - k1] = split_hi(b, a);
                         }
-                        v[0] = cpk(cre(v[0]), 0.0f);                    // imag[0] = 0
+                        v[0] = cpk(fmaf(0.0f, cim(v[0]), cre(v[0])), 0.0f);   // imag[0] = 0; a NaN there reaches real[0] in the reference (NaN * 0)
                         v[32] = cpk(0.0f, 0.0f);                        // real[n/2] = imag[0] (just zeroed), imag[n/2] = 0
                     } else {
                         const float4 *prow = reinterpret_cast<const float4 *>(X + (64 - t) * B::XP);

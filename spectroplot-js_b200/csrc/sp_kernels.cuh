@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const Params p)
                         const float2 a = cun(v[j * C::RL + k]);
                         const float2 b = X[(N - bin) & (N - 1)];
                         float2 r;
-                        if (bin == 0) r = make_float2(a.x, 0.f);
+                        if (bin == 0) r = make_float2(fmaf(0.0f, a.y, a.x), 0.f); // a NaN in imag[0] reaches real[0] in the reference (its butterflies multiply by every twiddle, NaN * 0 = NaN): keep that
                         else if (bin == N / 2) r = make_float2(0.f, 0.f);
                         else if (bin < N / 2) r = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
                         else r = make_float2(0.5f * (b.y + a.y), 0.5f * (-b.x + a.x));
@@ -593,7 +593,7 @@ static __global__ void __launch_bounds__(256) spectrum_epilogue_kernel(const Par
         float2 r = X[bin];
         if (p.channel_mode) {
             const float2 a = r, b = X[(n - bin) & (n - 1)];
-            if (bin == 0) r = make_float2(a.x, 0.f);
+            if (bin == 0) r = make_float2(fmaf(0.0f, a.y, a.x), 0.f); // a NaN in imag[0] reaches real[0] in the reference (its butterflies multiply by every twiddle, NaN * 0 = NaN): keep that
             else if (bin == n / 2) r = make_float2(0.f, 0.f);
             else if (bin < n / 2) r = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
             else r = make_float2(0.5f * (b.y + a.y), 0.5f * (-b.x + a.x));

@@ -234,7 +234,43 @@ def host_fixtures(W):
     print("ref_host.json ok (%d windows, %d cmaps)" % (len(out["windows"]), len(out["cmaps"])))
 
 
+def random_cases(W, count=40, seed=20261017):
+    """Seeded random points of the option space at small sizes (the GPU suite has no access to the reference: these widen the
+    set of reference replies it is compared with)."""
+    import random
+    from spectro_b200.samples import SampleView
+    rnd = random.Random(seed)
+    fmts = list(O.FORMATS)
+    wins = ["rectangular", "bartlett", "hamming", "hann", "blackman", "blackmanHarris"]
+    made = 0
+    while made < count:
+        fmt = rnd.choice(fmts)
+        n = 1 << rnd.randint(3, 9)
+        width = rnd.choice([2, 3, 5, 8, 13, 24, 33, 40])
+        hop = rnd.choice([0.0, 0.4, 1.0, 1.0, 2.3])
+        S = n + int(hop * n * (width - 1)) + rnd.randint(0, 9)
+        buf = bytearray(synth(fmt, S, 0x5EC7F000 + made))
+        sv = SampleView(fmt)
+        ragged = rnd.random() < 0.2 and sv.sampleWidth > sv.elementSize
+        if ragged:
+            del buf[-sv.elementSize:]
+        nan = fmt == "CF32" and rnd.random() < 0.3
+        if nan:
+            a = np.frombuffer(bytes(buf), "<f4").copy(); a[rnd.randrange(len(a))] = np.nan; buf = bytearray(a.tobytes())
+        if len(buf) / sv.sampleWidth < n:
+            continue
+        window, gain, rng = rnd.choice(wins), rnd.choice([-10, 0, 6, 25]), rnd.choice([6, 30, 90, -30])
+        cm = injective_cmap(rnd.choice([2, 64, 256, 300]))
+        chm, wf = rnd.random() < 0.25, rnd.random() < 0.25
+        name = "rnd%02d_%s_n%d_w%d%s%s%s%s" % (made, fmt.lower(), n, width, "_split" if chm else "", "_wf" if wf else "",
+                                             "_ragged" if ragged else "", "_nan" if nan else "")
+        run_case(W, name, fmt, n, width, window, cm, gain, rng, bytes(buf), chm, wf)
+        made += 1
+
+
 if __name__ == "__main__":
+    sys.path.insert(0, os.path.join(ROOT, "spectroplot-js_b200"))
     W = RefWorker()
     host_fixtures(W)
     render_cases(W)
+    random_cases(W)
