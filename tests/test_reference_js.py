@@ -43,7 +43,7 @@ def same_float(a, b):
 
 
 def test_fixture_inventory():
-    assert len(CASES) >= 76 and os.path.exists(os.path.join(REF, "ref_host.json"))
+    assert len(CASES) >= 92 and os.path.exists(os.path.join(REF, "ref_host.json"))
     fmts = {canonical(load(p)["fmt"]) for p in CASES}
     assert fmts == {"CU4", "CS4", "CU8", "CS8", "CU12", "CS12", "CU16", "CS16", "CU32", "CS32", "CU64", "CS64", "CF32", "CF64"}
     assert {load(p)["window"] for p in CASES} == {"rectangular", "bartlett", "hamming", "hann", "blackman", "blackmanHarris"}

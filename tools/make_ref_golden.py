@@ -234,6 +234,35 @@ def host_fixtures(W):
     print("ref_host.json ok (%d windows, %d cmaps)" % (len(out["windows"]), len(out["cmaps"])))
 
 
+def random_cases_large(W, count=16, seed=777):
+    """The same at the sizes of the fused kernels (N = 1024 .. 4096: render_rc_kernel, render_r64_kernel and their waterfall /
+    split-real variants), widths that leave partial tiles, ragged tails and NaN samples."""
+    import random
+    from spectro_b200.samples import SampleView
+    rnd = random.Random(seed)
+    wins = ["rectangular", "bartlett", "hamming", "hann", "blackman", "blackmanHarris"]
+    for made in range(count):
+        fmt = rnd.choice(["CS16", "CU8", "CF32", "CS8", "CU12", "CS4", "CU16", "CF32"])
+        n = rnd.choice([1024, 2048, 4096, 4096])
+        width = rnd.choice([8, 9, 12, 16, 17])
+        hop = rnd.choice([0.5, 1.0, 1.0, 1.7])
+        S = n + int(hop * n * (width - 1)) + rnd.randint(0, 9)
+        buf = bytearray(synth(fmt, S, 0x5EC7F100 + made))
+        sv = SampleView(fmt)
+        ragged = rnd.random() < 0.3 and sv.sampleWidth > sv.elementSize
+        if ragged:
+            del buf[-sv.elementSize:]
+        nan = fmt == "CF32" and rnd.random() < 0.4
+        if nan:
+            a = np.frombuffer(bytes(buf), "<f4").copy(); a[rnd.randrange(len(a))] = np.nan; buf = bytearray(a.tobytes())
+        window, gain, rng = rnd.choice(wins), rnd.choice([0, 6, 25]), rnd.choice([30, 90, -30])
+        cm = injective_cmap(rnd.choice([64, 256, 256]))
+        chm, wf = rnd.random() < 0.4, rnd.random() < 0.4
+        name = "big%02d_%s_n%d_w%d%s%s%s%s" % (made, fmt.lower(), n, width, "_split" if chm else "", "_wf" if wf else "",
+                                             "_ragged" if ragged else "", "_nan" if nan else "")
+        run_case(W, name, fmt, n, width, window, cm, gain, rng, bytes(buf), chm, wf)
+
+
 def random_cases(W, count=40, seed=20261017):
     """Seeded random points of the option space at small sizes (the GPU suite has no access to the reference: these widen the
     set of reference replies it is compared with)."""
@@ -271,6 +300,8 @@ def random_cases(W, count=40, seed=20261017):
 if __name__ == "__main__":
     sys.path.insert(0, os.path.join(ROOT, "spectroplot-js_b200"))
     W = RefWorker()
-    host_fixtures(W)
-    render_cases(W)
-    random_cases(W)
+    if "--large-only" not in sys.argv:
+        host_fixtures(W)
+        render_cases(W)
+        random_cases(W)
+    random_cases_large(W)
