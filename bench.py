@@ -305,6 +305,14 @@ def run_ours(args):
     else:
         m_hist = d_hist
     c_total = int(m_hist[1000:].sum().item())
+    if args.kernel_only:
+        if rank == 0:
+            kms = float(np.mean(kern_ms)) if len(kern_ms) else ms_step
+            peak, _ = measured_peaks()
+            emit({"lib": os.environ.get("SP_LIB", "default"), "ms_per_step": ms_step, "kernel_ms": kms,
+                  "frac": ALG_BYTES_PER_SAMPLE * sh["sample_count"] / (kms * 1e-3) / 1e9 / peak, "value": value,
+                  "hist_ok": c_total == total_width * N_FFT, "clocks": clocks})
+        return 0
     assert c_total == total_width * N_FFT, (c_total, total_width * N_FFT)
 
     # ---- end to end through the host-buffer API (pinned host memory both ways)
@@ -399,6 +407,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--kernel-only", action="store_true",
+                    help="development: device-resident leg only (no e2e, no cpu leg, no output check) - A/B runs of experiment builds ($SP_LIB)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

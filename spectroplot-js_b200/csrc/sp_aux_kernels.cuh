@@ -24,17 +24,15 @@ __device__ __forceinline__ unsigned char u8clamped(double v)
 // Many CTAs of 256 frames each; the last CTA to finish converts the folded min/max to doubles.
 // `ordered` says fmin/fmax hold f2ord() encodings (sub-frame mode).  mm = {ordered min, ordered max,
 // done counter}, initialised by prep_kernel.
-// One launch that resets everything a render accumulates into: both histograms, the tile counters of the
-// fast kernel (one per launch of the render) and the min / max fold of finalize_kernel.
-constexpr int TILE_COUNTERS = 4096;
-__global__ void __launch_bounds__(256) prep_kernel(unsigned long long *cb, unsigned long long *c, int cmap_len, unsigned *tilectr, unsigned *mm,
+// One launch that resets everything a render accumulates into: both histograms, the joint histogram and the
+// min / max fold of finalize_kernel.
+__global__ void __launch_bounds__(256) prep_kernel(unsigned long long *cb, unsigned long long *c, int cmap_len, unsigned *mm,
                                                    unsigned long long *jh)
 {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i < CB_BINS) cb[i] = 0;
     if (i < JH_SIZE) jh[i] = 0;
     if (i < cmap_len) c[i] = 0;
-    if (i < TILE_COUNTERS) tilectr[i] = 0;
     if (i == 0) {
         mm[0] = f2ord(0.0f);        // lib/worker.js:35
         mm[1] = f2ord(-200.0f);     // lib/worker.js:36

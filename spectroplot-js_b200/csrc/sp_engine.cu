@@ -5,7 +5,6 @@
 // No CPU fallback exists: without an sm_100 device sp_create fails with SP_E_NO_DEVICE.
 #include "../../include/spectro_b200.h"
 #include "sp_aux_kernels.cuh"
-#include "sp_kernel_fast.cuh"
 #include "sp_kernel_r64.cuh"
 
 #include <cmath>
@@ -25,16 +24,14 @@ using sp::Params;
 #define SP_DECL(tag)                                                                                             \
     extern "C" cudaError_t sp_rl_##tag(int, const Params *, int, size_t, cudaStream_t, int *) __attribute__((weak)); \
     extern "C" cudaError_t sp_pl_##tag(int, const Params *, float2 *, const float2 *, cudaStream_t) __attribute__((weak)); \
-    extern "C" cudaError_t sp_fl_##tag(int, const Params *, int, cudaStream_t, unsigned *, const float2 *, const float2 *, int *) __attribute__((weak)); \
-    extern "C" cudaError_t sp_r64_##tag(int, const Params *, int, cudaStream_t, unsigned *, const float2 *, int *) __attribute__((weak)); \
+    extern "C" cudaError_t sp_r64_##tag(int, const Params *, int, cudaStream_t, const float2 *, const CUtensorMap *, int *) __attribute__((weak)); \
     extern "C" cudaError_t sp_rc_##tag(int, const Params *, int, cudaStream_t, const float2 *, int *) __attribute__((weak));
 SP_DECL(rt) SP_DECL(cu4) SP_DECL(cs4) SP_DECL(cu8) SP_DECL(cs8) SP_DECL(cu12) SP_DECL(cs12) SP_DECL(cu16)
 SP_DECL(cs16) SP_DECL(cu32) SP_DECL(cs32) SP_DECL(cu64) SP_DECL(cs64) SP_DECL(cf32) SP_DECL(cf64)
 
 typedef cudaError_t (*render_fn)(int, const Params *, int, size_t, cudaStream_t, int *);
 typedef cudaError_t (*prepass_fn)(int, const Params *, float2 *, const float2 *, cudaStream_t);
-typedef cudaError_t (*fast_fn)(int, const Params *, int, cudaStream_t, unsigned *, const float2 *, const float2 *, int *);
-typedef cudaError_t (*r64_fn)(int, const Params *, int, cudaStream_t, unsigned *, const float2 *, int *);
+typedef cudaError_t (*r64_fn)(int, const Params *, int, cudaStream_t, const float2 *, const CUtensorMap *, int *);
 typedef cudaError_t (*rc_fn)(int, const Params *, int, cudaStream_t, const float2 *, int *);
 
 static render_fn render_for(int fmt)
@@ -48,12 +45,6 @@ static prepass_fn prepass_for(int fmt)
     static const prepass_fn tab[SP_FORMAT_COUNT] = { sp_pl_cu4, sp_pl_cs4, sp_pl_cu8, sp_pl_cs8, sp_pl_cu12, sp_pl_cs12,
         sp_pl_cu16, sp_pl_cs16, sp_pl_cu32, sp_pl_cs32, sp_pl_cu64, sp_pl_cs64, sp_pl_cf32, sp_pl_cf64 };
     return tab[fmt] ? tab[fmt] : sp_pl_rt;
-}
-static fast_fn fast_for(int fmt)
-{
-    static const fast_fn tab[SP_FORMAT_COUNT] = { sp_fl_cu4, sp_fl_cs4, sp_fl_cu8, sp_fl_cs8, sp_fl_cu12, sp_fl_cs12,
-        sp_fl_cu16, sp_fl_cs16, sp_fl_cu32, sp_fl_cs32, sp_fl_cu64, sp_fl_cs64, sp_fl_cf32, sp_fl_cf64 };
-    return tab[fmt] ? tab[fmt] : sp_fl_rt;
 }
 static r64_fn r64_for(int fmt)
 {
@@ -113,21 +104,20 @@ struct sp_engine {
     std::string err;
     std::string plan;
     std::map<int, float2 *> tw, twA, twB;    // twiddle tables by n (full / pass A / pass B)
-    DevBuf tilectr, pin[2], pimg[2];         // pipeline: double-buffered input bytes / image tiles
+    DevBuf pin[2], pimg[2];                  // pipeline: double-buffered input bytes / image tiles
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_comp[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr }, ev_setup = nullptr;
-    DevBuf in, zin, spec, image, fmin, fmax, fmid, gauges, hist, jhist, stats, mm, lut, window, scratch, db, synth_lut;
+    DevBuf in, zin, spec, image, fmin, fmax, fmid, gauges, hist, jhist, stats, mm, lut, window, window_t, scratch, db, synth_lut;
     // state of an enqueued (not yet finished) render
     std::vector<cudaEvent_t> prof0, prof1;   // per-launch timing ring of the render kernel
     long long prof_count = 0;
-    std::vector<float> h_window;             // last uploaded window / LUT (upload only on change)
+    std::vector<float> h_window, h_window_t; // last uploaded window / LUT (upload only on change)
     std::vector<uint32_t> h_lut;
     double *stats_src = nullptr;
     bool pending = false;
     long long pend_width = 0;
     int pend_cmap_len = 0;
     int launches = 0;
-    int ctr_next = 0;                        // next unused tile counter (reset by prep_kernel)
 };
 
 static thread_local std::string g_create_err;
@@ -238,7 +228,7 @@ extern "C" void sp_destroy(sp_engine *e)
     for (auto &kv : e->twA) cudaFree(kv.second);
     for (auto &kv : e->twB) cudaFree(kv.second);
     DevBuf *bufs[] = { &e->in, &e->zin, &e->spec, &e->image, &e->fmin, &e->fmax, &e->fmid, &e->gauges, &e->hist, &e->jhist, &e->stats, &e->mm,
-                       &e->lut, &e->window, &e->scratch, &e->db, &e->synth_lut, &e->tilectr, &e->pin[0], &e->pin[1],
+                       &e->lut, &e->window, &e->window_t, &e->scratch, &e->db, &e->synth_lut, &e->pin[0], &e->pin[1],
                        &e->pimg[0], &e->pimg[1] };
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (auto ev : e->prof0) cudaEventDestroy(ev);
@@ -326,20 +316,6 @@ static int get_pass_tables(sp_engine *e, int log2k, const float2 **twA, const fl
     return SP_OK;
 }
 
-// fast-path tables: tw6A [256][6] = W_4096^{t*k}, tw6B [16][6] = W_256^{b*k}, k = 1, 2, 3, 4, 8, 12
-static int get_fast_tables(sp_engine *e, const float2 **tw6A, const float2 **tw6B)
-{
-    static const int ks[6] = { 1, 2, 3, 4, 8, 12 };
-    auto ia = e->twA.find(-4096), ib = e->twB.find(-256);
-    if (ia != e->twA.end() && ib != e->twB.end()) { *tw6A = ia->second; *tw6B = ib->second; return SP_OK; }
-    std::vector<float2> ha((size_t)256 * 6), hb((size_t)16 * 6);
-    for (int t = 0; t < 256; t++) for (int i = 0; i < 6; i++) ha[(size_t)t * 6 + i] = twid((long long)t * ks[i], 4096);
-    for (int b = 0; b < 16; b++) for (int i = 0; i < 6; i++) hb[(size_t)b * 6 + i] = twid((long long)b * ks[i], 256);
-    int rc = upload_table(e, e->twA, -4096, ha, tw6A);
-    if (rc) return rc;
-    return upload_table(e, e->twB, -256, hb, tw6B);
-}
-
 // 64 x 64 path table: tw14 [64][14] = W_4096^{t*k}, k = 1..7, 8, 16, .., 56
 static int get_r64_table(sp_engine *e, const float2 **tw14)
 {
@@ -351,13 +327,6 @@ static int get_r64_table(sp_engine *e, const float2 **tw14)
     return upload_table(e, e->twA, -64, h, tw14);
 }
 
-// Which N = 4096 spectrogram kernel: SP_FAST=r64 (default: the 64 x 64 kernel, 16-frame tiles) or SP_FAST=dbx (the
-// 16 x 16 x 16 kernel, 8-frame tiles); SP_NO_FAST disables both.
-static bool use_r64()
-{
-    static const char *v = getenv("SP_FAST");
-    return !(v && !strcmp(v, "dbx"));
-}
 // 64 x C path table (N = 512, 1024, 2048): tw14 [C][14] = W_N^{t*k}, k = 1..7, 8, 16, .., 56
 static int get_rc_table(sp_engine *e, int n, const float2 **tw14)
 {
@@ -407,17 +376,15 @@ extern "C" const char *sp_kernel_plan(sp_engine *e, int format, int n, int chann
     snprintf(buf, sizeof buf, "%s%srender_kernel<N=%d,%s> tile=%d frames smem_x=%d B%s", pl.sub_r > 1 ? "prepass_kernel<R=" : "",
              pl.sub_r > 1 ? (std::to_string(pl.sub_r) + "> + ").c_str() : "", 1 << pl.log2k,
              specialised(format) ? k_names[format] : "runtime-format", pl.tile, pl.smem_x * 8, channel_mode ? " +splitreal" : "");
-    if (pl.log2k >= 8 && pl.log2k <= 11 && !channel_mode && !getenv("SP_NO_FAST") && use_r64() && rc_for(format) && sp::sample_width(format) <= 8) {
+    if (pl.log2k >= 8 && pl.log2k <= 11 && !channel_mode && !getenv("SP_NO_FAST") && rc_for(format) && sp::sample_width(format) <= 8) {
         const size_t l = strlen(buf);
         snprintf(buf + l, sizeof buf - l, " | fast path (spectrogram and waterfall): render_rc_kernel<N=64x%d, tile=%d frames> (one exchange, joint histogram, TMA-staged input)",
                  (1 << pl.log2k) / 64, 65536 >> pl.log2k);
     }
     if (pl.log2k == 12 && !channel_mode && !getenv("SP_NO_FAST")) {
         const size_t l = strlen(buf);
-        if (use_r64() && (pl.sub_r > 1 ? sp_r64_cf32 != nullptr : r64_for(format) != nullptr) && (pl.sub_r > 1 || sp::sample_width(format) <= 8))
+        if ((pl.sub_r > 1 ? sp_r64_cf32 != nullptr : r64_for(format) != nullptr) && (pl.sub_r > 1 || sp::sample_width(format) <= 8))
             snprintf(buf + l, sizeof buf - l, " | fast path (spectrogram and waterfall): render_r64_kernel<streams=4,tile=16 frames> (64x64 FFT, one exchange, joint histogram, TMA-staged input)");
-        else
-            snprintf(buf + l, sizeof buf - l, " | spectrogram fast path: render_fast_kernel<slots=2,frames=8> (TMA-staged input, packed fp32)");
     }
     e->plan = buf;
     return e->plan.c_str();
@@ -546,6 +513,15 @@ static int prepare(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, boo
             for (int i = 0; i < n; i++) e->h_window[i] = (float)rq->windowc[i] * wscale;
             if ((rc = ensure(e, e->window, sizeof(float) * (size_t)n))) return rc;
             CU(cudaMemcpyAsync(e->window.p, e->h_window.data(), sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+            if (n == 4096) {
+                // render_r64_kernel reads its 64 coefficients per thread straight from global memory (L1-resident): [16][64] float4,
+                // element (q, t) = w[64*(4q + i) + t], so that a warp's LDG.128 covers 512 contiguous bytes
+                e->h_window_t.resize(4096);
+                for (int q = 0; q < 16; q++) for (int t = 0; t < 64; t++) for (int i = 0; i < 4; i++)
+                    e->h_window_t[(size_t)(q * 64 + t) * 4 + i] = e->h_window[(size_t)64 * (4 * q + i) + t];
+                if ((rc = ensure(e, e->window_t, sizeof(float) * 4096))) return rc;
+                CU(cudaMemcpyAsync(e->window_t.p, e->h_window_t.data(), sizeof(float) * 4096, cudaMemcpyHostToDevice, e->stream));
+            }
         }
         if (!same_l) {
             e->h_lut.resize((size_t)rq->cmap_len);
@@ -557,6 +533,7 @@ static int prepare(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, boo
         }
     }
     p.window = (const float *)e->window.p;
+    p.window_t = (const float4 *)e->window_t.p;
     p.lut = (const uint32_t *)e->lut.p;
     if ((rc = get_pass_tables(e, j.plan.log2k, &p.twA, &p.twB))) return rc;
 
@@ -620,13 +597,6 @@ static int prepare(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, boo
     return SP_OK;
 }
 
-// N = 4096 fast path (render_fast_kernel): spectrogram layout, cmap_len <= 256, width % 8 == 0, image wanted.
-static bool fast_eligible(const Params &p)
-{
-    static const bool off = getenv("SP_NO_FAST") != nullptr;
-    return !off && p.image && !p.waterfall && !p.channel_mode && !p.db_out && p.cmap_len <= 256 && (p.nframes % 8 == 0) &&
-           (p.chunk_first % 8 == 0) && (((uintptr_t)p.image) & 31) == 0;
-}
 // render_r64_kernel / render_rc_kernel: any width (rows that are not 32-byte aligned are written word by word), so the
 // same frames take the same kernel whether a message is rendered in one piece, in pipeline chunks or in shards
 static bool fused_eligible(const Params &p, bool waterfall_ok = false, bool split_ok = false)
@@ -635,44 +605,32 @@ static bool fused_eligible(const Params &p, bool waterfall_ok = false, bool spli
     return !off && p.image && (!p.waterfall || waterfall_ok) && (!p.channel_mode || split_ok) && !p.db_out && p.cmap_len <= 256 && (p.chunk_first % 8 == 0) &&
            (((uintptr_t)p.image) & 3) == 0;
 }
-// Frames [0, *nfast) of the chunk described by q go through the fast kernel: whole tiles of 8 frames that
-// lie entirely inside the buffer (the kernel carries no per-frame predicates); the caller renders the rest.
-static int launch_fast_kernel(sp_engine *e, fast_fn fn, Params &q, long long *nfast)
+// Tensor map of the [n rows][width] RGBA picture for the store warps of render_r64_kernel: boxes of 32 rows x 8 pixels,
+// 32-byte swizzle.  The encoder is a driver entry point; it is resolved at run time so that the library keeps linking the
+// CUDA runtime only.
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn tensor_map_encoder()
 {
-    const bool sub = q.sub_r > 1;
-    long long nf = q.chunk_frames / 8 * 8;
-    if (!sub) {
-        const long long sw = sp::sample_width(q.format);
-        auto inside = [&](long long xr) {
-            const long long xgl = q.frame_first + q.chunk_first + xr;
-            const long long p0 = (long long)(0.5 + q.stride * (double)xgl) - q.sample_base;       // lib/worker.js:72
-            return p0 >= 0 && (unsigned long long)(p0 + 4096) * (unsigned long long)sw <= q.valid_bytes;
-        };
-        while (nf > 0 && !inside(nf - 1)) nf -= 8;
-        if (nf > 0 && !inside(0)) nf = 0;
-    }
-    *nfast = nf;
-    if (nf == 0) return SP_OK;
-    const float2 *tw6A = nullptr, *tw6B = nullptr;
-    int rc = get_fast_tables(e, &tw6A, &tw6B), occ = 0;
-    if (rc) return rc;
-    CU(fn(sub ? 1 : 0, &q, 0, e->stream, nullptr, tw6A, tw6B, &occ));
-    if (occ < 1) return fail(e, SP_E_CUDA, "render_fast_kernel does not fit an SM");
-    if (e->ctr_next == sp::TILE_COUNTERS) {                // one counter per fast-kernel launch of this render
-        CU(cudaMemsetAsync(e->tilectr.p, 0, 4 * sp::TILE_COUNTERS, e->stream));
-        e->ctr_next = 0;
-    }
-    unsigned *ctr = (unsigned *)e->tilectr.p + e->ctr_next++;
-    Params r = q;
-    r.chunk_frames = nf;
-    r.ntiles = (nf / 8) * (sub ? q.sub_r : 1);
-    const long long want = (r.ntiles + 1) / 2;
-    const int grid = (int)(want < e->sm_count ? want : e->sm_count);
-    prof_begin(e);
-    CU(fn(sub ? 1 : 0, &r, grid, e->stream, ctr, tw6A, tw6B, nullptr));
-    prof_end(e);
-    e->launches++;
-    return SP_OK;
+    static encode_tiled_fn fn = []() -> encode_tiled_fn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) return nullptr;
+        return (encode_tiled_fn)p;
+    }();
+    return fn;
+}
+static bool image_tensor_map(CUtensorMap *tm, uint8_t *image, long long width, int rows)
+{
+    static const bool off = getenv("SP_NO_TMA_STORE") != nullptr;
+    encode_tiled_fn enc = tensor_map_encoder();
+    if (off || !enc || !image || width % 8 != 0 || ((uintptr_t)image & 31) != 0 || width > 0x7fffffffLL) return false;
+    const cuuint64_t dims[2] = { (cuuint64_t)width, (cuuint64_t)rows };
+    const cuuint64_t strides[1] = { (cuuint64_t)width * 4 };
+    const cuuint32_t box[2] = { 8, 32 }, estr[2] = { 1, 1 };
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, image, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // Frames [0, *nfast) of the chunk described by q go through render_r64_kernel: every group of 8 frames that lies inside the buffer
@@ -697,19 +655,17 @@ static int launch_r64_kernel(sp_engine *e, r64_fn fn, Params &q, long long *nfas
     const float2 *tw14 = nullptr;
     int rc = get_r64_table(e, &tw14), occ = 0;
     if (rc) return rc;
-    CU(fn(sub ? 1 : 0, &q, 0, e->stream, nullptr, tw14, &occ));
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof tm);
+    CU(fn(sub ? 1 : 0, &q, 0, e->stream, tw14, &tm, &occ));
     if (occ < 1) { *nfast = 0; return SP_OK; }             // not built for this format: the caller falls back
-    if (e->ctr_next == sp::TILE_COUNTERS) {
-        CU(cudaMemsetAsync(e->tilectr.p, 0, 4 * sp::TILE_COUNTERS, e->stream));
-        e->ctr_next = 0;
-    }
-    unsigned *ctr = (unsigned *)e->tilectr.p + e->ctr_next++;
     Params r = q;
     r.chunk_frames = nf;
     r.ntiles = ((nf + 15) / 16) * (sub ? q.sub_r : 1);
+    r.use_tma = (!sub && !r.waterfall && image_tensor_map(&tm, r.image, r.nframes, r.n_full)) ? 1 : 0;
     const int grid = (int)(r.ntiles < e->sm_count ? r.ntiles : e->sm_count);
     prof_begin(e);
-    CU(fn(sub ? 1 : 0, &r, grid, e->stream, ctr, tw14, nullptr));
+    CU(fn(sub ? 1 : 0, &r, grid, e->stream, tw14, &tm, nullptr));
     prof_end(e);
     e->launches++;
     return SP_OK;
@@ -750,12 +706,8 @@ static int launch_rc_kernel(sp_engine *e, rc_fn fn, int log2n, Params &q, long l
 static int enqueue_begin(sp_engine *e, Job &j)
 {
     e->launches = 0;
-    int rc = ensure(e, e->tilectr, 4 * sp::TILE_COUNTERS);
-    if (rc) return rc;
     CU(cudaEventRecord(e->ev0, e->stream));
-    sp::prep_kernel<<<(SP_MAX_CMAP + 255) / 256, 256, 0, e->stream>>>(j.d_cb, j.d_c, j.p.cmap_len, (unsigned *)e->tilectr.p, (unsigned *)e->mm.p,
-                                                                          (unsigned long long *)e->jhist.p);
-    e->ctr_next = 0;
+    sp::prep_kernel<<<(SP_MAX_CMAP + 255) / 256, 256, 0, e->stream>>>(j.d_cb, j.d_c, j.p.cmap_len, (unsigned *)e->mm.p, (unsigned long long *)e->jhist.p);
     e->launches++;
     return SP_OK;
 }
@@ -768,23 +720,16 @@ static int enqueue_frames(sp_engine *e, Job &j, Params &p)
     int occ = 0;
     if (j.plan.sub_r == 1) {
         Params q = p;
-        if (j.plan.log2k == 12 && fused_eligible(p, /* waterfall rows in the store warps */ true, /* split-real in the FFT warps */ true) && use_r64() && r64_for(fmt)) {
+        if (j.plan.log2k == 12 && fused_eligible(p, /* waterfall rows in the store warps */ true, /* split-real in the FFT warps */ true) && r64_for(fmt)) {
             long long nfast = 0;
             int rc = launch_r64_kernel(e, r64_for(fmt), q, &nfast);
             if (rc) return rc;
             q.chunk_first += nfast;
             q.chunk_frames -= nfast;
         }
-        if (j.plan.log2k >= 8 && j.plan.log2k <= 11 && fused_eligible(p, true) && use_r64() && rc_for(fmt)) {
+        if (j.plan.log2k >= 8 && j.plan.log2k <= 11 && fused_eligible(p, true) && rc_for(fmt)) {
             long long nfast = 0;
             int rc = launch_rc_kernel(e, rc_for(fmt), j.plan.log2k, q, &nfast);
-            if (rc) return rc;
-            q.chunk_first += nfast;
-            q.chunk_frames -= nfast;
-        }
-        if (j.plan.log2k == 12 && fast_eligible(q) && fast_for(fmt) && q.chunk_frames >= 8) {
-            long long nfast = 0;
-            int rc = launch_fast_kernel(e, fast_for(fmt), q, &nfast);
             if (rc) return rc;
             q.chunk_first += nfast;
             q.chunk_frames -= nfast;
@@ -840,20 +785,12 @@ static int enqueue_frames(sp_engine *e, Job &j, Params &p)
             q.chunk_frames = (nf - c0 < ch) ? nf - c0 : ch;
             CU(pf(R, &q, (float2 *)e->scratch.p, tw_full, e->stream));
             q.sub_in = (const float2 *)e->scratch.p;
-            fast_fn ff = sp_fl_cf32 ? sp_fl_cf32 : sp_fl_rt;
             e->launches++;
             Params full = q;                                   // what the epilogue kernel sees
             if (tap) { q.spec_out = (float2 *)e->spec.p; q.image = nullptr; q.db_out = nullptr; q.channel_mode = 0; }
-            if (fused_eligible(q) && use_r64() && sp_r64_cf32) {
+            if (fused_eligible(q) && sp_r64_cf32) {
                 long long nfast = 0;
                 if ((rc = launch_r64_kernel(e, sp_r64_cf32, q, &nfast))) return rc;
-                q.sub_in += (size_t)nfast * (size_t)R * 4096;
-                q.chunk_first += nfast;
-                q.chunk_frames -= nfast;
-            }
-            if (fast_eligible(q) && ff && q.chunk_frames >= 8) {
-                long long nfast = 0;
-                if ((rc = launch_fast_kernel(e, ff, q, &nfast))) return rc;
                 q.sub_in += (size_t)nfast * (size_t)R * 4096;
                 q.chunk_first += nfast;
                 q.chunk_frames -= nfast;

@@ -4,7 +4,6 @@
 // specialised formats next to the runtime-switch variant (tag "rt").
 #pragma once
 #include "sp_kernels.cuh"
-#include "sp_kernel_fast.cuh"
 #include "sp_kernel_r64.cuh"
 #include "sp_kernel_rc.cuh"
 
@@ -72,33 +71,9 @@ static cudaError_t launch_prepass(int r, const Params &p, float2 *out, const flo
     return cudaGetLastError();
 }
 
-// N = 4096 fast path: one CTA of 2 x 256 threads per SM, 8 frames per tile (sp_kernel_fast.cuh).
-template <int FMT, bool SUB>
-static cudaError_t launch_fast_v(const Params &p, int grid, cudaStream_t st, unsigned *tile_counter, const float2 *tw6A,
-                                 const float2 *tw6B, int *occ_out)
-{
-    using B = FastCfg<FMT, SUB>;
-    auto kfn = render_fast_kernel<FMT, SUB>;
-    static bool attr_flags[64] = {};
-    bool &attr_done = attr_flag(attr_flags);
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
-    if (occ_out) {
-        int nb = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, B::THREADS, B::SMEM_BYTES);
-        *occ_out = nb;
-        return e;
-    }
-    kfn<<<grid, B::THREADS, B::SMEM_BYTES, st>>>(p, tw6A, tw6B, tile_counter);
-    return cudaGetLastError();
-}
-
 // N = 4096 "64 x 64" path: one CTA of 4 x 64 threads per SM, 16 frames per tile (sp_kernel_r64.cuh).
 template <int FMT, bool SUB, bool OPT>
-static cudaError_t launch_r64_k(const Params &p, int grid, cudaStream_t st, unsigned *tile_counter, const float2 *tw14, int *occ_out)
+static cudaError_t launch_r64_k(const Params &p, int grid, cudaStream_t st, const float2 *tw14, const CUtensorMap *tm, int *occ_out)
 {
     using B = R64Cfg<FMT, SUB>;
     auto kfn = render_r64_kernel<FMT, SUB, OPT>;
@@ -115,22 +90,22 @@ static cudaError_t launch_r64_k(const Params &p, int grid, cudaStream_t st, unsi
         *occ_out = nb;
         return e;
     }
-    kfn<<<grid, B::THREADS, B::SMEM_BYTES, st>>>(p, tw14, tile_counter);
+    kfn<<<grid, B::THREADS, B::SMEM_BYTES, st>>>(p, tw14, *tm);
     return cudaGetLastError();
 }
 template <int FMT, bool SUB>
-static cudaError_t launch_r64_v(const Params &p, int grid, cudaStream_t st, unsigned *tile_counter, const float2 *tw14, int *occ_out)
+static cudaError_t launch_r64_v(const Params &p, int grid, cudaStream_t st, const float2 *tw14, const CUtensorMap *tm, int *occ_out)
 {
     using B = R64Cfg<FMT, SUB>;
     if constexpr (!B::OK) {
         if (occ_out) *occ_out = 0;
         return occ_out ? cudaSuccess : cudaErrorInvalidValue;
     } else if constexpr (SUB) {
-        return launch_r64_k<FMT, true, false>(p, grid, st, tile_counter, tw14, occ_out);
+        return launch_r64_k<FMT, true, false>(p, grid, st, tw14, tm, occ_out);
     } else {
         // messages that ask for the waterfall layout or the split-real post-process take the kernel compiled with them
-        if (p.waterfall || p.channel_mode) return launch_r64_k<FMT, false, true>(p, grid, st, tile_counter, tw14, occ_out);
-        return launch_r64_k<FMT, false, false>(p, grid, st, tile_counter, tw14, occ_out);
+        if (p.waterfall || p.channel_mode) return launch_r64_k<FMT, false, true>(p, grid, st, tw14, tm, occ_out);
+        return launch_r64_k<FMT, false, false>(p, grid, st, tw14, tm, occ_out);
     }
 }
 
@@ -173,22 +148,12 @@ extern "C" cudaError_t SP_CAT(sp_rl_, SP_INST_TAG)(int log2n, const sp::Params *
 {
     return sp::launch_render<SP_INST_FMT>(log2n, *p, grid, smem, st, occ_out);
 }
-extern "C" cudaError_t SP_CAT(sp_fl_, SP_INST_TAG)(int sub, const sp::Params *p, int grid, cudaStream_t st, unsigned *tile_counter,
-                                                    const float2 *tw6A, const float2 *tw6B, int *occ_out)
-{
-    // sub-frame input (four-step path) is always complex fp32: only those two instances carry the SUB variant
-    if constexpr (SP_INST_FMT == sp::CF32 || SP_INST_FMT == sp::FMT_RUNTIME) {
-        if (sub) return sp::launch_fast_v<SP_INST_FMT, true>(*p, grid, st, tile_counter, tw6A, tw6B, occ_out);
-    } else if (sub) return cudaErrorInvalidValue;
-    return sp::launch_fast_v<SP_INST_FMT, false>(*p, grid, st, tile_counter, tw6A, tw6B, occ_out);
-}
-extern "C" cudaError_t SP_CAT(sp_r64_, SP_INST_TAG)(int sub, const sp::Params *p, int grid, cudaStream_t st, unsigned *tile_counter,
-                                                     const float2 *tw14, int *occ_out)
+extern "C" cudaError_t SP_CAT(sp_r64_, SP_INST_TAG)(int sub, const sp::Params *p, int grid, cudaStream_t st, const float2 *tw14, const CUtensorMap *tm, int *occ_out)
 {
     if constexpr (SP_INST_FMT == sp::CF32 || SP_INST_FMT == sp::FMT_RUNTIME) {
-        if (sub) return sp::launch_r64_v<SP_INST_FMT, true>(*p, grid, st, tile_counter, tw14, occ_out);
+        if (sub) return sp::launch_r64_v<SP_INST_FMT, true>(*p, grid, st, tw14, tm, occ_out);
     } else if (sub) return cudaErrorInvalidValue;
-    return sp::launch_r64_v<SP_INST_FMT, false>(*p, grid, st, tile_counter, tw14, occ_out);
+    return sp::launch_r64_v<SP_INST_FMT, false>(*p, grid, st, tw14, tm, occ_out);
 }
 extern "C" cudaError_t SP_CAT(sp_rc_, SP_INST_TAG)(int log2n, const sp::Params *p, int grid, cudaStream_t st, const float2 *tw14, int *occ_out)
 {

@@ -1,8 +1,8 @@
 // sp_kernel_r64.cuh — the N = 4096 "64 x 64" render kernel: the headline size, and the second stage of
 // the four-step path for N = 8192..65536.
 //
-// Why another N = 4096 kernel: ncu on the 16 x 16 x 16 kernel (profiles/r01_ncu_summary_s4a_dbx.txt)
-// shows the L1/shared-memory data pipe as the binding unit (22.5 wavefronts per 32 samples: two
+// Design note: ncu on the round-1 16 x 16 x 16 kernel (profiles/r01_ncu_summary_s4a_dbx.txt, since deleted)
+// showed the L1/shared-memory data pipe as the binding unit (22.5 wavefronts per 32 samples: two
 // exchanges = 8, two histogram atomics = 3.6, window + twiddle tables = 2.5, scattered 32-byte row
 // stores = 4.3, ...).  This kernel is built around that number:
 //   * 4096 = 64 x 64: a thread holds 64 complex points, a frame is transformed by 64 threads with
@@ -24,7 +24,17 @@
 // Replaces the hot loops of reference lib/worker.js:68-137 (+ lib/samples.js:313-400,
 // lib/fft_nayuki.js:54-96).
 #pragma once
-#include "sp_kernel_fast.cuh"
+#include "sp_prims.cuh"
+
+#ifndef SP_R64_ONEDFT
+#define SP_R64_ONEDFT 1
+#endif
+#ifndef SP_XP
+#define SP_XP 0             // timing-only experiment switches (wrong output): 1 conflict-free histogram addresses, 2 no histogram atomics,
+#endif                      // 4 no window, 8 no product twiddles, 16 no log2 / joint index
+#ifndef SP_R64_TMA
+#define SP_R64_TMA 1        // image rows through RGBA tiles + cp.async.bulk.tensor stores, window coefficients from L1-cached global memory
+#endif
 
 namespace sp {
 
@@ -39,8 +49,13 @@ template <int FMT, bool SUB> struct R64Cfg {
     static constexpr int WIN_PITCH = 64;                                         // floats per thread row, rotated by 4*t (conflict-free LDS.128)
     static constexpr int TW_PITCH = 14;                                          // float2 per thread row: w^1..w^7, w^8, w^16 .. w^56
     static constexpr int ST_PITCH = 1026;                                        // staging words per frame (1024 used)
+    // SP_R64_TMA: the 16 KB the window table took hold the store warps' RGBA tiles (one 4 KB tile per warp: four boxes of
+    // 32 rows x 8 frames), and the window comes from global memory (p.window_t, 16 KB: it stays in the 28 KB of L1 that the
+    // shared-memory carve-out leaves, because nothing else of this kernel goes through L1 any more)
+    static constexpr bool TMA = SP_R64_TMA != 0;
+    static constexpr int TILE_BYTES = TMA ? (STORE_THREADS / 32) * 4096 : 0;
     static constexpr size_t SMEM_BYTES = (size_t)STREAMS * X_BYTES + (size_t)F * ST_PITCH * 4 + (size_t)JH_SIZE * 4
-                                       + (SUB ? 0 : (size_t)T * WIN_PITCH * 4) + (size_t)T * TW_PITCH * 8 + 1024 /* LUT */
+                                       + ((SUB || TMA) ? 0 : (size_t)T * WIN_PITCH * 4) + TILE_BYTES + (size_t)T * TW_PITCH * 8 + 1024 /* LUT */
                                        + (size_t)F * 2 * 8 + 128 + 1024 /* LUT alignment */;
 };
 
@@ -73,8 +88,7 @@ __device__ __forceinline__ void stream_barrier(int stream)
 // the waterfall rows and the split-real post-process compiled in (selected by the launcher when a message asks for them),
 // so that the options cost the plain kernel neither registers nor instruction-cache footprint.
 template <int FMT, bool SUB, bool OPT = false>
-__global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, const float2 *__restrict__ tw14,
-                                                            unsigned *__restrict__ tile_counter)
+__global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, const float2 *__restrict__ tw14, const __grid_constant__ CUtensorMap tmap)
 {
     using B = R64Cfg<FMT, SUB>;
     constexpr int N = B::N, T = B::T, F = B::F;
@@ -85,10 +99,11 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
     const unsigned lut_base = (smem_u32(smem_r64) + 1023u) & ~1023u;
     unsigned char *s_x = smem_r64 + (lut_base - smem_u32(smem_r64)) + 1024;           // [4][X_BYTES] exchange / raw frame
     unsigned *s_lut = reinterpret_cast<unsigned *>(s_x - 1024);                       // [256] RGBA indexed by the staged byte (cmax - g, or g when range < 0)
-    unsigned *s_stage = reinterpret_cast<unsigned *>(s_x + B::STREAMS * B::X_BYTES);  // [16][1026] colour bytes (4 bins per word)
+    unsigned char *s_tiles = s_x + B::STREAMS * B::X_BYTES;                          // [4 store warps][4 boxes][32 rows][32 B] RGBA, 1 KB aligned (SP_R64_TMA)
+    unsigned *s_stage = reinterpret_cast<unsigned *>(s_tiles + B::TILE_BYTES);       // [16][1026] colour bytes (4 bins per word)
     unsigned *s_jh = s_stage + F * B::ST_PITCH;                                       // [JH_SIZE] joint histogram
     float *s_win = reinterpret_cast<float *>(s_jh + JH_SIZE);                         // [64][64] (row t: window[64 a + t] at (a + 4t) mod 64)
-    float2 *s_tw = reinterpret_cast<float2 *>(s_win + (SUB ? 0 : T * B::WIN_PITCH));  // [64][14]
+    float2 *s_tw = reinterpret_cast<float2 *>(s_win + ((SUB || B::TMA) ? 0 : T * B::WIN_PITCH));  // [64][14]
     uint2 *s_mm = reinterpret_cast<uint2 *>(s_tw + T * B::TW_PITCH);                  // [16][2] per-warp min/max bit patterns of |X|^2
     uint64_t *s_mbar = reinterpret_cast<uint64_t *>(s_mm + F * 2);                    // [4]
     int *s_off = reinterpret_cast<int *>(s_mbar + B::STREAMS);                        // [4][2] misalignment of the staged frame
@@ -107,7 +122,7 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
     const JhConst jc = jh_const(p);
     for (int i = tid; i < 256; i += B::THREADS) s_lut[i] = i <= cmax ? p.lut[jc.rev ? cmax - i : i] : 0u;
     for (int i = tid; i < T * B::TW_PITCH; i += B::THREADS) s_tw[i] = tw14[i];
-    if constexpr (!SUB)
+    if constexpr (!SUB && !B::TMA)
         for (int i = tid; i < N; i += B::THREADS) s_win[(i & 63) * B::WIN_PITCH + (((i >> 6) + 4 * (i & 63)) & 63)] = p.window[i];
     const unsigned jh_base = smem_u32(s_jh) - (JH_MAGIC_BITS << 2);      // address of joint bin j = S.bits * 4 + jh_base (mod 2^32)
     const int nfull = p.n_full, sub_r = p.sub_r;
@@ -134,7 +149,7 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
     // tile -> first chunk-relative frame, sub-sequence
     auto tile_xr0 = [&](long long tile) -> long long { return (SUB ? tile / sub_r : tile) * F; };
 
-    (void)tile_counter;                     // tiles are dealt round-robin: every stream of the CTA walks the same list without a barrier
+    // tiles are dealt round-robin: every stream of the CTA walks the same list without a barrier
     if (t == 0 && tid < B::FFT_THREADS) mbar_init(mbar, 1);
     if (tid == 0) {
         for (int h = 0; h < 2; h++) { mbar_init(s_full + h, B::FFT_THREADS / 32); mbar_init(s_empty + h, B::STORE_THREADS / 32); }
@@ -177,8 +192,51 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
                         }
                     }
                 }
+                if constexpr (B::TMA && !SUB) {
+                    if (p.use_tma && live && (!OPT || !p.waterfall)) {
+                        // RGBA tiles + tensor-TMA stores.  In iteration i this warp holds bins kb .. kb + 31 (kb = 32*(w & 1) + 64*(4m + j))
+                        // for j = 0..3: four boxes of 32 consecutive image rows y0 .. y0 + 31, y0 = (n/2 - kb - 31) mod n (row r of a
+                        // box is bin kb + 31 - r), each row 8 frames = 32 bytes.  The tile uses the 32-byte TMA swizzle (16-byte chunk
+                        // index ^= bit 2 of the row), which makes the STS.128 below bank-conflict free.  The one box that would wrap
+                        // (kb = n/2: bin n/2 is row 0, its neighbours rows n-1, n-2, ...) is placed at y0 = n - 31, where row 31 falls
+                        // outside the tensor and is clipped by the TMA unit; that row is written by its lane directly.
+                        const int lane = ht & 31, wq = ht >> 5;
+                        unsigned char *tile = s_tiles + wq * 4096;
+                        const int r = 31 - lane;
+                        const unsigned toff = (unsigned)(r * 32 + (((r >> 2) & 1) << 4));
 #pragma unroll 1
-                for (int i = 0; i < ((live && (!OPT || SUB || !p.waterfall)) ? 8 : 0); i++) {
+                        for (int i = 0; i < 8; i++) {
+                            const int id = ht + B::STORE_THREADS * i, k0 = id & 63, m = id >> 6;
+                            const unsigned *src = s_stage + (8 * h) * B::ST_PITCH + m * 64 + k0;
+                            unsigned w[8];
+#pragma unroll
+                            for (int f = 0; f < 8; f++) w[f] = src[f * B::ST_PITCH];
+                            if (lane == 0) bulk_wait_read0();              // the previous iteration's boxes have left the tile
+                            __syncwarp();
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                uint4 a, b;
+                                a.x = lut_at(lut_base, w[0], j); a.y = lut_at(lut_base, w[1], j); a.z = lut_at(lut_base, w[2], j); a.w = lut_at(lut_base, w[3], j);
+                                b.x = lut_at(lut_base, w[4], j); b.y = lut_at(lut_base, w[5], j); b.z = lut_at(lut_base, w[6], j); b.w = lut_at(lut_base, w[7], j);
+                                *reinterpret_cast<uint4 *>(tile + j * 1024 + toff) = a;
+                                *reinterpret_cast<uint4 *>(tile + j * 1024 + (toff ^ 16u)) = b;
+                                if (k0 + 64 * (4 * m + j) == N / 2)        // bin n/2 -> image row 0
+                                    st_global_256(reinterpret_cast<uint32_t *>(p.image) + x0, a, b);
+                            }
+                            fence_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                const int kb0 = (k0 & 32) + 256 * m;       // kb of j = 0
+#pragma unroll
+                                for (int j = 0; j < 4; j++)
+                                    tma_store_2d(&tmap, smem_u32(tile + j * 1024), (int)x0, (N / 2 - (kb0 + 64 * j) - 31) & (N - 1));
+                                bulk_commit();
+                            }
+                        }
+                    }
+                }
+#pragma unroll 1
+                for (int i = 0; i < ((live && (!OPT || SUB || !p.waterfall) && !(B::TMA && !SUB && p.use_tma)) ? 8 : 0); i++) {
                     // bins k0 + 64*(4m + j), j = 0..3, of the half's 8 frames: one 32-byte sector per row
                     const int id = ht + B::STORE_THREADS * i, k0 = id & 63, m = id >> 6;
                     const unsigned *src = s_stage + (8 * h) * B::ST_PITCH + m * 64 + k0;
@@ -216,6 +274,7 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
                 if ((ht & 31) == 0) mbar_arrive(s_empty + h);
             }
         }
+        if constexpr (B::TMA && !SUB) bulk_wait_read0();        // the tiles must outlive the last tensor stores
     } else {
     // ================= FFT warps: four frame streams =================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(B::FFT_REGS));
@@ -239,198 +298,219 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
             // produced a misaligned mbarrier address)
             asm volatile("" : "+r"(half));
             cf v[64];
-            // ---------------- load + decode + window (lib/worker.js:70-75) ----------------
-            mbar_wait(mbar, fpar);
-            if constexpr (SUB) {
-#pragma unroll
-                for (int a = 0; a < 64; a++) v[a] = cld(reinterpret_cast<const float2 *>(raw) + T * a + t);
-            } else {
-                const unsigned char *rp = raw + s_off[s * 2 + fpar];
-#pragma unroll
-                for (int a = 0; a < 64; a++) v[a] = decode_raw_cf<FMT>(rp, T * a + t, p.format);
-                // raw sample at p0 + n/2 (lib/worker.js:131-133); the power-of-two scale is exact
-                if (t == 0 && valid) p.fmid[p.chunk_first + xr0 + fl] = make_float2(cre(v[32]) * raw_scale<FMT>(), cim(v[32]) * raw_scale<FMT>());
-                const float4 *wrow = reinterpret_cast<const float4 *>(s_win + t * B::WIN_PITCH);
-#pragma unroll
-                for (int q = 0; q < 16; q++) {
-                    const float4 w = wrow[(q + t) & 15];
-                    v[4 * q] = cscale(v[4 * q], w.x);         v[4 * q + 1] = cscale(v[4 * q + 1], w.y);
-                    v[4 * q + 2] = cscale(v[4 * q + 2], w.z); v[4 * q + 3] = cscale(v[4 * q + 3], w.w);
-                }
-            }
-            fpar ^= 1;
-
-            // ---------------- pass A: DFT-64 over the slow input digit, twiddle W_4096^{t*k0} ----------------
-            dft<64>(v);
-            {
-                const float4 *twp = reinterpret_cast<const float4 *>(s_tw + t * B::TW_PITCH);
-                float2 w[8];                                            // w[j] = W^{t*j}, j = 1..7
-                {
-                    const float4 a = twp[0], b = twp[1], c = twp[2], d = twp[3];
-                    w[1] = make_float2(a.x, a.y); w[2] = make_float2(a.z, a.w); w[3] = make_float2(b.x, b.y); w[4] = make_float2(b.z, b.w);
-                    w[5] = make_float2(c.x, c.y); w[6] = make_float2(c.z, c.w); w[7] = make_float2(d.x, d.y);
-#pragma unroll
-                    for (int j = 1; j < 8; j++) v[j] = cmul(v[j], w[j]);
-                    float2 hi[8];                                       // hi[i] = W^{t*8i}, i = 1..7
-                    hi[1] = make_float2(d.z, d.w);
-                    const float4 e = twp[4], f = twp[5], g = twp[6];
-                    hi[2] = make_float2(e.x, e.y); hi[3] = make_float2(e.z, e.w); hi[4] = make_float2(f.x, f.y);
-                    hi[5] = make_float2(f.z, f.w); hi[6] = make_float2(g.x, g.y); hi[7] = make_float2(g.z, g.w);
-#pragma unroll
-                    for (int i = 1; i < 8; i++) {
-                        v[8 * i] = cmul(v[8 * i], hi[i]);
-#pragma unroll
-                        for (int j = 1; j < 8; j++) v[8 * i + j] = cmul(v[8 * i + j], cun(cmul(cpk(hi[i]), w[j])));
-                    }
-                }
-            }
-            stream_barrier(s);                                          // every thread of the stream has consumed the raw frame
-#pragma unroll
-            for (int k = 0; k < 64; k++) cst(X + k * B::XP + t, v[k]);  // Z[k0][t]
-            stream_barrier(s);
-            // ---------------- pass B: thread k0 = t, DFT-64 over b ----------------
-            {
-                const float4 *row = reinterpret_cast<const float4 *>(X + t * B::XP);
-#pragma unroll
-                for (int m = 0; m < 32; m++) {
-                    const float4 q = row[m];
-                    v[2 * m] = cpk(q.x, q.y); v[2 * m + 1] = cpk(q.z, q.w);
-                }
-            }
-            stream_barrier(s);                                          // the exchange buffer is free: prefetch the stream's next frame
+            // ONE copy of the 64-point transform in the instruction stream: the frame step is a two-trip loop around it
+            // (trip 0: load + pass A + exchange, trip 1: pass B + epilogue), which takes 7 KB of SASS out of the loop body
+            // (43 KB -> 38 KB against a 32 KB instruction cache shared by four streams in different phases).
+            // SP_R64_ONEDFT=0 unrolls the two trips again (the round-1 instruction stream).
+#if SP_R64_ONEDFT
+            int npass = 2;
+            asm volatile("" : "+r"(npass));
+#else
+            constexpr int npass = 2;
+#endif
             const bool split = OPT && !SUB && p.channel_mode;           // split-real needs the buffer once more, see below
             auto prefetch = [&]() {
                 if (step < B::STEPS - 1) stage(xr0 + fl + B::STREAMS, k0sub, fpar);
                 else if (next_tile < p.ntiles) stage(tile_xr0(next_tile) + s, SUB ? (int)(next_tile % sub_r) : 0, fpar);
             };
-            if (t == 0 && !split) prefetch();
-            // first frame of this stream in staging half step/2: the store warps must be done with the half (previous tile)
-            if ((step & 1) == 0) mbar_wait(s_empty + half, (kk + 1) & 1);
-            dft<64>(v);                                                 // v[k1] is bin t + 64*k1
-            if constexpr (OPT && !SUB) {
-                if (split) {
-                    // ---------------- split-real post-process (lib/fft_nayuki.js:103-119) ----------------
-                    // bin i = t + 64*k1 pairs with bin n - i = (64 - t) + 64*(63 - k1): thread 64 - t, register 63 - k1 (thread 0
-                    // pairs with itself, register 64 - k1).  One more pass through the exchange buffer: rows written with
-                    // STS.128, the partner's row read back reversed with LDS.128 (both conflict-free at this pitch).
-                    auto split_lo = [](cf a, cf b) {                    // i < n/2:  (re_i + re_p, im_i - im_p) / 2
-                        const float2 fb = cun(b);
-                        return cscale(cadd(a, cpk(fb.x, -fb.y)), 0.5f);
-                    };
-                    auto split_hi = [](cf a, cf b) {                    // i > n/2:  (im_p + im_i, -re_p + re_i) / 2, p = n - i
-                        const float2 fa = cun(a), fb = cun(b);
-                        return cscale(cadd(cpk(fa.y, fa.x), cpk(fb.y, -fb.x)), 0.5f);
-                    };
-                    {
-                        float4 *wrow = reinterpret_cast<float4 *>(X + t * B::XP);
+#if SP_R64_ONEDFT
+#pragma unroll 1
+#else
 #pragma unroll
-                        for (int m = 0; m < 32; m++) {
-                            const float2 a = cun(v[2 * m]), b = cun(v[2 * m + 1]);
-                            wrow[m] = make_float4(a.x, a.y, b.x, b.y);
+#endif
+            for (int pass = 0; pass < npass; pass++) {
+                if (pass == 0) {
+                    // ---------------- load + decode + window (lib/worker.js:70-75) ----------------
+                    mbar_wait(mbar, fpar);
+                    if constexpr (SUB) {
+#pragma unroll
+                        for (int a = 0; a < 64; a++) v[a] = cld(reinterpret_cast<const float2 *>(raw) + T * a + t);
+                    } else {
+                        const unsigned char *rp = raw + s_off[s * 2 + fpar];
+#pragma unroll
+                        for (int a = 0; a < 64; a++) v[a] = decode_raw_cf<FMT>(rp, T * a + t, p.format);
+                        // raw sample at p0 + n/2 (lib/worker.js:131-133); the power-of-two scale is exact
+                        if (t == 0 && valid) p.fmid[p.chunk_first + xr0 + fl] = make_float2(cre(v[32]) * raw_scale<FMT>(), cim(v[32]) * raw_scale<FMT>());
+                        const float4 *wrow = B::TMA ? p.window_t + t : reinterpret_cast<const float4 *>(s_win + t * B::WIN_PITCH);
+#pragma unroll
+                        for (int q = 0; q < 16; q++) {
+                            const float4 w = (SP_XP & 4) ? make_float4(1.f, 1.f, 1.f, 1.f) : B::TMA ? __ldg(wrow + 64 * q) : wrow[(q + t) & 15];
+                            v[4 * q] = cscale(v[4 * q], w.x);         v[4 * q + 1] = cscale(v[4 * q + 1], w.y);
+                            v[4 * q + 2] = cscale(v[4 * q + 2], w.z); v[4 * q + 3] = cscale(v[4 * q + 3], w.w);
                         }
                     }
-                    stream_barrier(s);
-                    if (t == 0) {
+                    fpar ^= 1;
+
+                }
+                dft<64>(v);                                             // pass A over the slow input digit / pass B: v[k1] is bin t + 64*k1
+                if (pass == 0) {
+                    {
+                        const float4 *twp = reinterpret_cast<const float4 *>(s_tw + t * B::TW_PITCH);
+                        float2 w[8];                                            // w[j] = W^{t*j}, j = 1..7
+                        {
+                            const float4 a = twp[0], b = twp[1], c = twp[2], d = twp[3];
+                            w[1] = make_float2(a.x, a.y); w[2] = make_float2(a.z, a.w); w[3] = make_float2(b.x, b.y); w[4] = make_float2(b.z, b.w);
+                            w[5] = make_float2(c.x, c.y); w[6] = make_float2(c.z, c.w); w[7] = make_float2(d.x, d.y);
 #pragma unroll
-                        for (int k1 = 1; k1 < 32; k1++) {
-                            const cf a = v[k1], b = v[64 - k1];
-                            v[k1] = split_lo(a, b);
-                            v[64 - k1] = split_hi(b, a);
-                        }
-                        v[0] = cpk(fmaf(0.0f, cim(v[0]), cre(v[0])), 0.0f);   // imag[0] = 0; a NaN there reaches real[0] in the reference (NaN * 0)
-                        v[32] = cpk(0.0f, 0.0f);                        // real[n/2] = imag[0] (just zeroed), imag[n/2] = 0
-                    } else {
-                        const float4 *prow = reinterpret_cast<const float4 *>(X + (64 - t) * B::XP);
+                            for (int j = 1; j < 8; j++) v[j] = cmul(v[j], w[j]);
+                            float2 hi[8];                                       // hi[i] = W^{t*8i}, i = 1..7
+                            hi[1] = make_float2(d.z, d.w);
+                            const float4 e = twp[4], f = twp[5], g = twp[6];
+                            hi[2] = make_float2(e.x, e.y); hi[3] = make_float2(e.z, e.w); hi[4] = make_float2(f.x, f.y);
+                            hi[5] = make_float2(f.z, f.w); hi[6] = make_float2(g.x, g.y); hi[7] = make_float2(g.z, g.w);
 #pragma unroll
-                        for (int a = 0; a < 32; a++) {
-                            const float4 q = prow[31 - a];              // partner registers 62 - 2a (.xy) and 63 - 2a (.zw)
-                            if (a < 16) {
-                                v[2 * a] = split_lo(v[2 * a], cpk(q.z, q.w));
-                                v[2 * a + 1] = split_lo(v[2 * a + 1], cpk(q.x, q.y));
-                            } else {
-                                v[2 * a] = split_hi(v[2 * a], cpk(q.z, q.w));
-                                v[2 * a + 1] = split_hi(v[2 * a + 1], cpk(q.x, q.y));
+                            for (int i = 1; i < 8; i++) {
+                                v[8 * i] = cmul(v[8 * i], hi[i]);
+#pragma unroll
+                                for (int j = 1; j < 8; j++) v[8 * i + j] = cmul(v[8 * i + j], (SP_XP & 8) ? w[j] : cun(cmul(cpk(hi[i]), w[j])));
                             }
                         }
                     }
-                    stream_barrier(s);                                  // now the buffer is free
-                    if (t == 0) prefetch();
-                }
-            }
+                    stream_barrier(s);                                          // every thread of the stream has consumed the raw frame
+#pragma unroll
+                    for (int k = 0; k < 64; k++) cst(X + k * B::XP + t, v[k]);  // Z[k0][t]
+                    stream_barrier(s);
+                    // ---------------- pass B: thread k0 = t, DFT-64 over b ----------------
+                    {
+                        const float4 *row = reinterpret_cast<const float4 *>(X + t * B::XP);
+#pragma unroll
+                        for (int m = 0; m < 32; m++) {
+                            const float4 q = row[m];
+                            v[2 * m] = cpk(q.x, q.y); v[2 * m + 1] = cpk(q.z, q.w);
+                        }
+                    }
+                    stream_barrier(s);                                          // the exchange buffer is free: prefetch the stream's next frame
+                    if (t == 0 && !split) prefetch();
+                    // first frame of this stream in staging half step/2: the store warps must be done with the half (previous tile)
+                    if ((step & 1) == 0) mbar_wait(s_empty + half, (kk + 1) & 1);
+                } else {
+                    if constexpr (OPT && !SUB) {
+                        if (split) {
+                            // ---------------- split-real post-process (lib/fft_nayuki.js:103-119) ----------------
+                            // bin i = t + 64*k1 pairs with bin n - i = (64 - t) + 64*(63 - k1): thread 64 - t, register 63 - k1 (thread 0
+                            // pairs with itself, register 64 - k1).  One more pass through the exchange buffer: rows written with
+                            // STS.128, the partner's row read back reversed with LDS.128 (both conflict-free at this pitch).
+                            auto split_lo = [](cf a, cf b) {                    // i < n/2:  (re_i + re_p, im_i - im_p) / 2
+                                const float2 fb = cun(b);
+                                return cscale(cadd(a, cpk(fb.x, -fb.y)), 0.5f);
+                            };
+                            auto split_hi = [](cf a, cf b) {                    // i > n/2:  (im_p + im_i, -re_p + re_i) / 2, p = n - i
+                                const float2 fa = cun(a), fb = cun(b);
+                                return cscale(cadd(cpk(fa.y, fa.x), cpk(fb.y, -fb.x)), 0.5f);
+                            };
+                            {
+                                float4 *wrow = reinterpret_cast<float4 *>(X + t * B::XP);
+#pragma unroll
+                                for (int m = 0; m < 32; m++) {
+                                    const float2 a = cun(v[2 * m]), b = cun(v[2 * m + 1]);
+                                    wrow[m] = make_float4(a.x, a.y, b.x, b.y);
+                                }
+                            }
+                            stream_barrier(s);
+                            if (t == 0) {
+#pragma unroll
+                                for (int k1 = 1; k1 < 32; k1++) {
+                                    const cf a = v[k1], b = v[64 - k1];
+                                    v[k1] = split_lo(a, b);
+                                    v[64 - k1] = split_hi(b, a);
+                                }
+                                v[0] = cpk(fmaf(0.0f, cim(v[0]), cre(v[0])), 0.0f);   // imag[0] = 0; a NaN there reaches real[0] in the reference (NaN * 0)
+                                v[32] = cpk(0.0f, 0.0f);                        // real[n/2] = imag[0] (just zeroed), imag[n/2] = 0
+                            } else {
+                                const float4 *prow = reinterpret_cast<const float4 *>(X + (64 - t) * B::XP);
+#pragma unroll
+                                for (int a = 0; a < 32; a++) {
+                                    const float4 q = prow[31 - a];              // partner registers 62 - 2a (.xy) and 63 - 2a (.zw)
+                                    if (a < 16) {
+                                        v[2 * a] = split_lo(v[2 * a], cpk(q.z, q.w));
+                                        v[2 * a + 1] = split_lo(v[2 * a + 1], cpk(q.x, q.y));
+                                    } else {
+                                        v[2 * a] = split_hi(v[2 * a], cpk(q.z, q.w));
+                                        v[2 * a + 1] = split_hi(v[2 * a + 1], cpk(q.x, q.y));
+                                    }
+                                }
+                            }
+                            stream_barrier(s);                                  // now the buffer is free
+                            if (t == 0) prefetch();
+                        }
+                    }
 
-            // ---------------- per-bin epilogue (lib/worker.js:85-122) ----------------
-            float amin = __int_as_float(0x7f800000), amax = 0.0f, prev = 0.0f;
-            unsigned umin_i = 0x7f800000u, umax_i = 0u;
-            unsigned *stg = s_stage + fl * B::ST_PITCH + t;
+                    // ---------------- per-bin epilogue (lib/worker.js:85-122) ----------------
+                    float amin = __int_as_float(0x7f800000), amax = 0.0f, prev = 0.0f;
+                    unsigned umin_i = 0x7f800000u, umax_i = 0u;
+                    unsigned *stg = s_stage + fl * B::ST_PITCH + t;
 #pragma unroll
-            for (int m = 0; m < 16; m++) {
-                unsigned yb[4];
+                    for (int m = 0; m < 16; m++) {
+                        unsigned yb[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float2 vi = cun(v[4 * m + j]);
-                    const float abs2 = fmaf(vi.x, vi.x, vi.y * vi.y);
+                        for (int j = 0; j < 4; j++) {
+                            const float2 vi = cun(v[4 * m + j]);
+                            const float abs2 = fmaf(vi.x, vi.x, vi.y * vi.y);
+                            if constexpr (FLOAT_IN) {
+                                // unsigned order on the bit patterns: a NaN wins the max (and is sorted out below), never the min
+                                umin_i = min(umin_i, __float_as_uint(abs2));
+                                umax_i = max(umax_i, __float_as_uint(abs2));
+                            } else if (j & 1) {                          // 3-input min / max: one FMNMX3 per two bins
+                                amin = fmin3(amin, prev, abs2);
+                                amax = fmax3(amax, prev, abs2);
+                            } else prev = abs2;
+                            const float l2 = (SP_XP & 16) ? abs2 : fast_log2(abs2);
+                            float Y;
+                            const float S = (SP_XP & 16) ? (Y = l2, __uint_as_float((__float_as_uint(l2) >> 20) + JH_MAGIC_BITS)) : jh_eval(l2, jc, Y);          // 2^23 + joint index, 2^23 + (cmax - colour index)
+                            if constexpr ((SP_XP & 1) != 0) red_shared_inc_addr(smem_u32(s_jh) + ((tid & 31) << 2) + (__float_as_uint(S) & 0x380u));
+                            else if constexpr (!(SP_XP & 2)) red_shared_inc_addr(jbase + (__float_as_uint(S) << 2));
+                            yb[j] = __float_as_uint(Y);
+                        }
+                        // bins t + 64*(4m .. 4m+3) of frame fl: four colour bytes in one word
+                        stg[m * 64] = __byte_perm(__byte_perm(yb[0], yb[1], 0x0040), __byte_perm(yb[2], yb[3], 0x0040), 0x5410);
+                    }
+                    unsigned umn, umx;
                     if constexpr (FLOAT_IN) {
-                        // unsigned order on the bit patterns: a NaN wins the max (and is sorted out below), never the min
-                        umin_i = min(umin_i, __float_as_uint(abs2));
-                        umax_i = max(umax_i, __float_as_uint(abs2));
-                    } else if (j & 1) {                          // 3-input min / max: one FMNMX3 per two bins
-                        amin = fmin3(amin, prev, abs2);
-                        amax = fmax3(amax, prev, abs2);
-                    } else prev = abs2;
-                    const float l2 = fast_log2(abs2);
-                    float Y;
-                    const float S = jh_eval(l2, jc, Y);          // 2^23 + joint index, 2^23 + (cmax - colour index)
-                    red_shared_inc_addr(jbase + (__float_as_uint(S) << 2));
-                    yb[j] = __float_as_uint(Y);
-                }
-                // bins t + 64*(4m .. 4m+3) of frame fl: four colour bytes in one word
-                stg[m * 64] = __byte_perm(__byte_perm(yb[0], yb[1], 0x0040), __byte_perm(yb[2], yb[3], 0x0040), 0x5410);
-            }
-            unsigned umn, umx;
-            if constexpr (FLOAT_IN) {
-                umn = __reduce_min_sync(0xffffffffu, umin_i);
-                umx = __reduce_max_sync(0xffffffffu, umax_i);
-            } else {
-                // |X|^2 >= 0: the bit patterns order like the values
-                umn = __reduce_min_sync(0xffffffffu, __float_as_uint(amin));
-                umx = __reduce_max_sync(0xffffffffu, __float_as_uint(amax));
-            }
-            if (umn < 0x00800000u || umx >= 0x7f800000u) {
-                // rare (warp-uniform): the frame holds |X|^2 == 0 (flushed: d0 = -inf), +inf or NaN.  Count them for
-                // the bin-0 fix-ups (lib/worker.js:105-106: ~~(+-Infinity) == ~~NaN == 0) and redo min / max the way
-                // the reference's `<` / `>` see them (NaN never wins).
-                unsigned nzero = 0, nbad = 0, nnan = 0;
-                float mn = __int_as_float(0x7f800000), mx = 0.0f;
+                        umn = __reduce_min_sync(0xffffffffu, umin_i);
+                        umx = __reduce_max_sync(0xffffffffu, umax_i);
+                    } else {
+                        // |X|^2 >= 0: the bit patterns order like the values
+                        umn = __reduce_min_sync(0xffffffffu, __float_as_uint(amin));
+                        umx = __reduce_max_sync(0xffffffffu, __float_as_uint(amax));
+                    }
+                    if (umn < 0x00800000u || umx >= 0x7f800000u) {
+                        // rare (warp-uniform): the frame holds |X|^2 == 0 (flushed: d0 = -inf), +inf or NaN.  Count them for
+                        // the bin-0 fix-ups (lib/worker.js:105-106: ~~(+-Infinity) == ~~NaN == 0) and redo min / max the way
+                        // the reference's `<` / `>` see them (NaN never wins).
+                        unsigned nzero = 0, nbad = 0, nnan = 0;
+                        float mn = __int_as_float(0x7f800000), mx = 0.0f;
 #pragma unroll
-                for (int i = 0; i < 64; i++) {
-                    const float2 vi = cun(v[i]);
-                    const float abs2 = fmaf(vi.x, vi.x, vi.y * vi.y);
-                    nzero += abs2 < 1.17549435e-38f ? 1u : 0u;
-                    nbad += !(abs2 <= 3.402823466e38f) ? 1u : 0u;
-                    nnan += abs2 != abs2 ? 1u : 0u;
-                    mn = fminf(mn, abs2 < 1.17549435e-38f ? 0.0f : abs2);
-                    mx = fmaxf(mx, abs2);
-                }
-                nzero = __reduce_add_sync(0xffffffffu, nzero);
-                nbad = __reduce_add_sync(0xffffffffu, nbad);
-                nnan = __reduce_add_sync(0xffffffffu, nnan);
-                umn = __reduce_min_sync(0xffffffffu, __float_as_uint(mn));
-                umx = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
-                if ((t & 31) == 0 && valid) {
-                    if (nzero) atomicAdd(&s_jh[JH_ZERO], nzero);
-                    if (nbad) atomicAdd(&s_jh[JH_BAD], nbad);
-                    if (nnan) {                 // NaN pixels were counted under the joint index sat(NaN) = 0 yields: move them
-                        float Yn;
-                        const float Sn = jh_eval(__int_as_float(0x7fffffff), jc, Yn);
-                        atomicSub(&s_jh[__float_as_uint(Sn) - JH_MAGIC_BITS], nnan);
-                        atomicAdd(&s_jh[JH_NAN], nnan);
+                        for (int i = 0; i < 64; i++) {
+                            const float2 vi = cun(v[i]);
+                            const float abs2 = fmaf(vi.x, vi.x, vi.y * vi.y);
+                            nzero += abs2 < 1.17549435e-38f ? 1u : 0u;
+                            nbad += !(abs2 <= 3.402823466e38f) ? 1u : 0u;
+                            nnan += abs2 != abs2 ? 1u : 0u;
+                            mn = fminf(mn, abs2 < 1.17549435e-38f ? 0.0f : abs2);
+                            mx = fmaxf(mx, abs2);
+                        }
+                        nzero = __reduce_add_sync(0xffffffffu, nzero);
+                        nbad = __reduce_add_sync(0xffffffffu, nbad);
+                        nnan = __reduce_add_sync(0xffffffffu, nnan);
+                        umn = __reduce_min_sync(0xffffffffu, __float_as_uint(mn));
+                        umx = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+                        if ((t & 31) == 0 && valid) {
+                            if (nzero) atomicAdd(&s_jh[JH_ZERO], nzero);
+                            if (nbad) atomicAdd(&s_jh[JH_BAD], nbad);
+                            if (nnan) {                 // NaN pixels were counted under the joint index sat(NaN) = 0 yields: move them
+                                float Yn;
+                                const float Sn = jh_eval(__int_as_float(0x7fffffff), jc, Yn);
+                                atomicSub(&s_jh[__float_as_uint(Sn) - JH_MAGIC_BITS], nnan);
+                                atomicAdd(&s_jh[JH_NAN], nnan);
+                            }
+                        }
+                    }
+                    if ((t & 31) == 0) s_mm[fl * 2 + (t >> 5)] = make_uint2(umn, umx);
+                    if (step & 1) {                 // this warp has staged its last frame of half step/2 (and its s_mm entries)
+                        __syncwarp();
+                        if ((t & 31) == 0) mbar_arrive(s_full + half);
                     }
                 }
-            }
-            if ((t & 31) == 0) s_mm[fl * 2 + (t >> 5)] = make_uint2(umn, umx);
-            if (step & 1) {                 // this warp has staged its last frame of half step/2 (and its s_mm entries)
-                __syncwarp();
-                if ((t & 31) == 0) mbar_arrive(s_full + half);
             }
         } // steps
         tile = next_tile;

@@ -28,6 +28,7 @@ struct Params {
     long long frame_first;         // global index of local frame 0
     long long nframes;             // frames rendered by this launch (image width in pixels)
     const float *window;           // n_full fp32 coefficients (rounded once from double)
+    const float4 *window_t;        // render_r64_kernel: the same coefficients as [16][64] float4, element (q, t) = w[64*(4q + i) + t], i = 0..3
     const float2 *twA;             // pass-A twiddles [15][T]:  W_N^{t*k},      k = 1..15 (N = kernel size, T = N/16)
     const float2 *twB;             // pass-B twiddles [15][RL]: W_{N/16}^{b*k}, k = 1..15 (3-pass sizes only)
     // dB / colour mapping
@@ -55,6 +56,7 @@ struct Params {
     // joint (dB bin, colour index) histogram of render_r64_kernel (decoded by finalize_kernel)
     unsigned long long *j_hist;    // [JH_SIZE]
     float jA, jB, jC, jD;          // see jh_eval()
+    int use_tma;                   // render_r64_kernel: image rows leave through tensor-TMA stores (width % 4 == 0, 16-byte aligned image)
     int dbg;                       // SP_DEBUG_SKIP bit mask (performance experiments only): 1 image stores, 4 LUT lookups (store warps of render_r64_kernel)
 };
 

@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "..", "lib", "libspectro_b200.so")
+# SP_LIB: an experiment build of the same C ABI (csrc/Makefile XFLAGS); the product default is the in-tree library
+LIB_PATH = os.environ.get("SP_LIB") or os.path.join(_HERE, "..", "lib", "libspectro_b200.so")
 
 CB_HIST_SIZE = 1000
 MAX_CMAP = 4096
