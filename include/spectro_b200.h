@@ -60,8 +60,10 @@ enum sp_error {
     SP_E_BAD_N = -2,        /* n is not a power of two (reference throws a string,
                                lib/fft_nayuki.js:38-39) or outside [SP_MIN_N, SP_MAX_N] */
     SP_E_BAD_FORMAT = -3,   /* format enum out of range                                */
-    SP_E_TOO_SHORT = -4,    /* sampleCount < n (reference would read undefined -> NaN) */
-    SP_E_BAD_WIDTH = -5,    /* width < 2 (stride divides by width-1, lib/worker.js:50) */
+    SP_E_TOO_SHORT = -4,    /* a SHARD of a message with sampleCount < n (a whole such message is
+                               rendered like the reference renders it: undefined -> NaN frames) */
+    SP_E_BAD_WIDTH = -5,    /* width < 1 (width == 1 renders one frame at sample 0 like
+                               lib/worker.js:50,72: stride = x/0, ~~(0.5 + NaN) == 0)   */
     SP_E_RAGGED = -6,       /* byte_length not a multiple of the typed-array element
                                size (the reference's `new Int16Array(buffer)` throws)  */
     SP_E_BAD_CMAP = -7,     /* cmap_len < 2 or > SP_MAX_CMAP                           */
@@ -72,8 +74,9 @@ enum sp_error {
     SP_E_NCCL = -12         /* multi-device merge failed                               */
 };
 
-#define SP_MIN_N 8          /* reference accepts any power of two; kernels cover 8..65536 */
-#define SP_MAX_N 65536
+#define SP_MIN_N 2          /* reference accepts any power of two (lib/fft_nayuki.js:38-39); kernels cover
+                               2..262144 (n = 1 draws nothing upstream: its row index n/2 - i is fractional) */
+#define SP_MAX_N 262144
 #define SP_CB_HIST_SIZE 1000 /* lib/worker.js:41: centi-Bel bins, 0.0 .. -100.0 dB        */
 #define SP_MAX_CMAP 4096     /* custom RGB[] maps of any length (lib/spectroplot.js:245)  */
 

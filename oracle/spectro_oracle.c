@@ -409,7 +409,9 @@ static int render_impl(const spo_request *rq, spo_reply *rp)
 int spo_render(const spo_request *rq, spo_reply *rp)
 {
     if (!rq) return -1;
-    if (rq->width < 2) return -5;
+    /* width == 1: stride = (sampleCount - n) / 0 is +-Infinity or NaN, stride * 0 is NaN and ~~NaN == 0
+     * (lib/worker.js:50,72): one frame at sample 0, which render_impl's own arithmetic reproduces */
+    if (rq->width < 1) return -5;
     return render_impl(rq, rp);
 }
 

@@ -478,4 +478,34 @@ template <> __device__ __forceinline__ void dft<64>(cf (&v)[64])
     for (int i = 0; i < 64; i++) v[i] = y[i];
 }
 
+// 32-point DFT in registers: n = 8*n1 + n0 (n1 < 4), k = k0 + 4*k1 :  W32^{nk} = W4^{n1 k0} * W32^{n0 k0} * W8^{n0 k1}
+template <int K0> __device__ __forceinline__ void dft32_twiddle_row(cf (&v)[32])
+{
+    // element v[8*K0 + n0] holds the k0 = K0 output of column n0: times W32^{n0*K0} = W64^{2*n0*K0}
+    v[8 * K0 + 1] = mul_w64<2 * 1 * K0>(v[8 * K0 + 1]); v[8 * K0 + 2] = mul_w64<2 * 2 * K0>(v[8 * K0 + 2]);
+    v[8 * K0 + 3] = mul_w64<2 * 3 * K0>(v[8 * K0 + 3]); v[8 * K0 + 4] = mul_w64<2 * 4 * K0>(v[8 * K0 + 4]);
+    v[8 * K0 + 5] = mul_w64<2 * 5 * K0>(v[8 * K0 + 5]); v[8 * K0 + 6] = mul_w64<2 * 6 * K0>(v[8 * K0 + 6]);
+    v[8 * K0 + 7] = mul_w64<2 * 7 * K0>(v[8 * K0 + 7]);
+}
+template <> __device__ __forceinline__ void dft<32>(cf (&v)[32])
+{
+#pragma unroll
+    for (int n0 = 0; n0 < 8; n0++) {                       // DFT-4 over n1 of column n0; result k0 -> v[8*k0 + n0]
+        dft4(v[n0], v[8 + n0], v[16 + n0], v[24 + n0]);
+    }
+    dft32_twiddle_row<1>(v); dft32_twiddle_row<2>(v); dft32_twiddle_row<3>(v);
+    cf y[32];
+#pragma unroll
+    for (int k0 = 0; k0 < 4; k0++) {                       // DFT-8 over n0 of row k0; result k1 -> bin k0 + 4*k1
+        cf u[8];
+#pragma unroll
+        for (int n0 = 0; n0 < 8; n0++) u[n0] = v[8 * k0 + n0];
+        dft<8>(u);
+#pragma unroll
+        for (int k1 = 0; k1 < 8; k1++) y[k0 + 4 * k1] = u[k1];
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = y[i];
+}
+
 } // namespace sp

@@ -356,6 +356,7 @@ static Plan make_plan(int log2n)
     Plan pl;
     if (log2n > 12) { pl.log2k = 12; pl.sub_r = 1 << (log2n - 12); } else pl.log2k = log2n;
     switch (pl.log2k) {
+    case 1: fill_cfg<1>(pl); break;   case 2: fill_cfg<2>(pl); break;
     case 3: fill_cfg<3>(pl); break;   case 4: fill_cfg<4>(pl); break;   case 5: fill_cfg<5>(pl); break;
     case 6: fill_cfg<6>(pl); break;   case 7: fill_cfg<7>(pl); break;   case 8: fill_cfg<8>(pl); break;
     case 9: fill_cfg<9>(pl); break;   case 10: fill_cfg<10>(pl); break; case 11: fill_cfg<11>(pl); break;
@@ -371,7 +372,7 @@ extern "C" const char *sp_kernel_plan(sp_engine *e, int format, int n, int chann
     if (!e) return "";
     const int l = ilog2_exact(n);
     char buf[384];
-    if (l < 3 || l > 16 || format < 0 || format >= SP_FORMAT_COUNT) { e->plan = "unsupported"; return e->plan.c_str(); }
+    if (l < 1 || l > 18 || format < 0 || format >= SP_FORMAT_COUNT) { e->plan = "unsupported"; return e->plan.c_str(); }
     Plan pl = make_plan(l);
     snprintf(buf, sizeof buf, "%s%srender_kernel<N=%d,%s> tile=%d frames smem_x=%d B%s", pl.sub_r > 1 ? "prepass_kernel<R=" : "",
              pl.sub_r > 1 ? (std::to_string(pl.sub_r) + "> + ").c_str() : "", 1 << pl.log2k,
@@ -427,16 +428,20 @@ static int validate(sp_engine *e, const sp_request *rq, bool shard, double *samp
     if (total_bytes % (uint64_t)sp::element_size(rq->format))
         return fail(e, SP_E_RAGGED, "byte length %llu is not a multiple of the %d-byte element size (typed array construction throws)",
                     (unsigned long long)total_bytes, sp::element_size(rq->format));
-    if (total_width < 2) return fail(e, SP_E_BAD_WIDTH, "width=%lld: need at least 2 frames", (long long)total_width);
-    if (rq->width < 1) return fail(e, SP_E_BAD_WIDTH, "width=%lld", (long long)rq->width);
+    if (total_width < 1 || rq->width < 1) return fail(e, SP_E_BAD_WIDTH, "width=%lld", (long long)(total_width < 1 ? total_width : rq->width));
     const double sc = (double)total_bytes / (double)sp::sample_width(rq->format);   // lib/samples.js:167
-    if (sc < (double)rq->n) return fail(e, SP_E_TOO_SHORT, "sampleCount %.1f < n %d", sc, rq->n);
+    // A capture shorter than one frame is answered like the reference answers it (it never throws): every frame reads
+    // `undefined` past the typed array and comes out as NaN / colour 0 through the bounds-checked decode.  Only a shard
+    // of such a message is refused (there is nothing to shard).
+    if (sc < (double)rq->n && shard) return fail(e, SP_E_TOO_SHORT, "sampleCount %.1f < n %d in a sharded message", sc, rq->n);
     if (!(rq->range != 0.0) || !std::isfinite(rq->range) || !std::isfinite(rq->gain) || !(rq->block_norm > 0.0))
         return fail(e, SP_E_INVAL, "range must be finite and non-zero, gain finite, block_norm > 0");
     if (10.0 * log10(rq->block_norm) < -75.0)
         return fail(e, SP_E_INVAL, "block_norm %.3g is below -75 dB (1/weight of any window up to n = 65536 is above -49 dB)", rq->block_norm);
     *sample_count = sc;
-    *stride = (sc - (double)rq->n) / (double)(total_width - 1);                      // lib/worker.js:50
+    // lib/worker.js:50.  A one-frame message divides by zero there: stride is +-Infinity or NaN, stride * 0 is NaN and
+    // ~~(0.5 + NaN) == 0, i.e. the frame starts at sample 0 - the same as stride 0.
+    *stride = total_width == 1 ? 0.0 : (sc - (double)rq->n) / (double)(total_width - 1);
     if (shard) {
         if (rq->frame_first < 0 || rq->frame_first + rq->width > total_width)
             return fail(e, SP_E_RANGE, "frame range [%lld, %lld) outside total width %lld", (long long)rq->frame_first,

@@ -42,6 +42,8 @@ template <int FMT>
 static cudaError_t launch_render(int log2n, const Params &p, int grid, size_t smem, cudaStream_t st, int *occ_out)
 {
     switch (log2n) {
+    case 1: return launch_one<1, FMT>(p, grid, smem, st, occ_out);
+    case 2: return launch_one<2, FMT>(p, grid, smem, st, occ_out);
     case 3: return launch_one<3, FMT>(p, grid, smem, st, occ_out);
     case 4: return launch_one<4, FMT>(p, grid, smem, st, occ_out);
     case 5: return launch_one<5, FMT>(p, grid, smem, st, occ_out);
@@ -66,6 +68,8 @@ static cudaError_t launch_prepass(int r, const Params &p, float2 *out, const flo
     case 4: prepass_kernel<4, FMT><<<grid, 256, 0, st>>>(p, out, tw_full); break;
     case 8: prepass_kernel<8, FMT><<<grid, 256, 0, st>>>(p, out, tw_full); break;
     case 16: prepass_kernel<16, FMT><<<grid, 256, 0, st>>>(p, out, tw_full); break;
+    case 32: prepass_kernel<32, FMT><<<grid, 256, 0, st>>>(p, out, tw_full); break;
+    case 64: prepass_kernel<64, FMT><<<grid, 256, 0, st>>>(p, out, tw_full); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

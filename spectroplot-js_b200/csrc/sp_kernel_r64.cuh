@@ -27,7 +27,7 @@
 #include "sp_prims.cuh"
 
 #ifndef SP_R64_ONEDFT
-#define SP_R64_ONEDFT 1
+#define SP_R64_ONEDFT 0        // measured: the two-trip loop is 5 % SLOWER (0.298 vs 0.283 ms, profiles/r02_ab_r64.txt): the scheduling barrier costs more than the smaller loop body saves
 #endif
 #ifndef SP_XP
 #define SP_XP 0             // timing-only experiment switches (wrong output): 1 conflict-free histogram addresses, 2 no histogram atomics,

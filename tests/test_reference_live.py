@@ -139,3 +139,35 @@ def test_worker_random_messages_equal_the_oracle():
         assert g("offset") == case
         checked += 1
     assert checked >= 60
+
+
+def test_worker_degenerate_messages_equal_the_oracle():
+    """Messages outside the worker's comfortable domain that the reference nevertheless answers (it never throws):
+    one frame (stride = x/0), captures shorter than one frame (every frame reads `undefined`), n = 2 and 4."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    from make_ref_golden import RefWorker, hist_to_np, injective_cmap
+    from oracle import oracle as O
+    W = RefWorker()
+    I = W.I
+    cases = [("CU8", 8, 1, 8), ("CU8", 8, 1, 20), ("CS16", 16, 4, 10), ("CF32", 32, 3, 5), ("CS8", 64, 2, 63),
+             ("CU8", 2, 7, 30), ("CS16", 4, 5, 21), ("CF32", 2, 2, 2), ("CU4", 4, 1, 3), ("CS12", 16, 3, 16)]
+    for k, (fmt, n, width, S) in enumerate(cases):
+        buf = O.synth(fmt, 0, S, S, 77 + k).tobytes()
+        windowc, weight = W.window("hann" if n > 2 else "rectangular", n)
+        cm = injective_cmap(256)
+        jcm = W.cmap(cm)
+        r = W.post(dict(block_norm=1.0 / weight, gain=6, range=30, cmap=jcm, n=n, windowc=windowc, width=width, offset=k,
+                        buffer=I.from_py(buf), format=fmt, channelMode=False, waterfall=False))
+        g = lambda key: I.get_prop(r, key)
+        cmb = np.array(I.to_py(jcm), np.uint8)
+        o = O.render(buf, fmt, n, width, np.array(I.to_py(windowc), np.float64), 1.0 / weight, 6, 30, cmb)
+        label = (fmt, n, width, S)
+        assert np.array_equal(I.get_prop(g("imageData"), "data").arr, o.image.reshape(-1)), label
+        assert np.array_equal(hist_to_np(I, g("cB_hist"))[0], o.cB_hist.astype(np.float64)), label
+        assert np.array_equal(hist_to_np(I, g("c_hist"))[0], o.c_hist.astype(np.float64)), label
+        for key in ("gauge_mins", "gauge_maxs", "gauge_amps"):
+            assert np.array_equal(g(key).arr, getattr(o, key)), label + (key,)
+        for key in ("dBfs_min", "dBfs_max"):
+            a, b = float(g(key)), float(getattr(o, key))
+            assert a == b or (a != a and b != b), label + (key, a, b)
