@@ -236,13 +236,33 @@ def test_error_codes(engine):
             engine.render(**a)
         return ei.value.name
     assert code(n=48, windowc=np.ones(48)) == "SP_E_BAD_N"           # 'Length is not a power of 2'
-    assert code(width=1) == "SP_E_BAD_WIDTH"
+    assert code(width=0) == "SP_E_BAD_WIDTH"
     assert code(buf=bytes(7)) == "SP_E_RAGGED"
-    assert code(buf=bytes(64)) == "SP_E_TOO_SHORT"
+    assert code(n=1, windowc=np.ones(1)) == "SP_E_BAD_N"
+    assert code(n=1 << 19, windowc=np.ones(1 << 19)) == "SP_E_BAD_N"
     assert code(cmap=CM256[:1]) == "SP_E_BAD_CMAP"
     assert code(fmt=99) == "SP_E_BAD_FORMAT"
     # and the engine still works afterwards
     engine.render(buf, "CS16", 64, 4, w, 1 / wt, 6, 30, CM256)
+
+
+@pytest.mark.parametrize("fmt,n,width,S", [("CU8", 8, 1, 8), ("CU8", 8, 1, 20), ("CS16", 16, 4, 10), ("CF32", 32, 3, 5), ("CS8", 64, 2, 63),
+                                           ("CU8", 2, 7, 30), ("CS16", 4, 5, 21), ("CF32", 2, 2, 2), ("CU4", 4, 1, 3), ("CS12", 16, 3, 16),
+                                           ("CS16", 4096, 3, 1000), ("CF32", 8192, 2, 5000), ("CS16", 2, 64, 640), ("CU8", 4, 100, 1000)])
+def test_degenerate_messages_are_answered_like_the_reference(engine, fmt, n, width, S):
+    """One frame (stride = x/0 -> frame at sample 0), captures shorter than a frame (every read past the array is
+    `undefined`), n = 2 and 4: the reference worker answers all of them (lib/worker.js:50,72), and so does the engine
+    (oracle pinned to the reference on these cases by tests/test_reference_live.py)."""
+    raw = O.synth(fmt, 0, S, S, 31 + n + width).tobytes()
+    run_both(engine, raw, fmt, n, width, "hann" if n > 2 else "rectangular", want_db=False)
+
+
+@pytest.mark.parametrize("n,width", [(131072, 8), (262144, 4)])
+def test_sizes_above_65536(engine, n, width):
+    """lib/fft_nayuki.js:38-39 accepts any power of two; the four-step path covers n up to 262144 (pre-pass radix 32 / 64)."""
+    S = n * 2 + 77
+    raw = O.synth("CS16", 0, S, S, 5).tobytes()
+    run_both(engine, raw, "CS16", n, width, "blackmanHarris", want_db=True)
 
 
 # ------------------------------------------------------------------ sharding: N shards == 1 shard, exactly
