@@ -6,6 +6,7 @@
 #include "../../include/spectro_b200.h"
 #include "sp_aux_kernels.cuh"
 #include "sp_kernel_r64.cuh"
+#include "sp_kernel_big.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -25,7 +26,8 @@ using sp::Params;
     extern "C" cudaError_t sp_rl_##tag(int, const Params *, int, size_t, cudaStream_t, int *) __attribute__((weak)); \
     extern "C" cudaError_t sp_pl_##tag(int, const Params *, float2 *, const float2 *, cudaStream_t) __attribute__((weak)); \
     extern "C" cudaError_t sp_r64_##tag(int, const Params *, int, cudaStream_t, const float2 *, const CUtensorMap *, int *) __attribute__((weak)); \
-    extern "C" cudaError_t sp_rc_##tag(int, const Params *, int, cudaStream_t, const float2 *, int *) __attribute__((weak));
+    extern "C" cudaError_t sp_rc_##tag(int, const Params *, int, cudaStream_t, const float2 *, int *) __attribute__((weak)); \
+    extern "C" cudaError_t sp_big_##tag(const Params *, const sp::BigArgs *, int, cudaStream_t, const float2 *, int *) __attribute__((weak));
 SP_DECL(rt) SP_DECL(cu4) SP_DECL(cs4) SP_DECL(cu8) SP_DECL(cs8) SP_DECL(cu12) SP_DECL(cs12) SP_DECL(cu16)
 SP_DECL(cs16) SP_DECL(cu32) SP_DECL(cs32) SP_DECL(cu64) SP_DECL(cs64) SP_DECL(cf32) SP_DECL(cf64)
 
@@ -33,6 +35,7 @@ typedef cudaError_t (*render_fn)(int, const Params *, int, size_t, cudaStream_t,
 typedef cudaError_t (*prepass_fn)(int, const Params *, float2 *, const float2 *, cudaStream_t);
 typedef cudaError_t (*r64_fn)(int, const Params *, int, cudaStream_t, const float2 *, const CUtensorMap *, int *);
 typedef cudaError_t (*rc_fn)(int, const Params *, int, cudaStream_t, const float2 *, int *);
+typedef cudaError_t (*big_fn)(const Params *, const sp::BigArgs *, int, cudaStream_t, const float2 *, int *);
 
 static render_fn render_for(int fmt)
 {
@@ -57,6 +60,12 @@ static rc_fn rc_for(int fmt)
     static const rc_fn tab[SP_FORMAT_COUNT] = { sp_rc_cu4, sp_rc_cs4, sp_rc_cu8, sp_rc_cs8, sp_rc_cu12, sp_rc_cs12,
         sp_rc_cu16, sp_rc_cs16, sp_rc_cu32, sp_rc_cs32, sp_rc_cu64, sp_rc_cs64, sp_rc_cf32, sp_rc_cf64 };
     return tab[fmt];
+}
+static big_fn big_for(int fmt)
+{
+    static const big_fn tab[SP_FORMAT_COUNT] = { sp_big_cu4, sp_big_cs4, sp_big_cu8, sp_big_cs8, sp_big_cu12, sp_big_cs12,
+        sp_big_cu16, sp_big_cs16, sp_big_cu32, sp_big_cs32, sp_big_cu64, sp_big_cs64, sp_big_cf32, sp_big_cf64 };
+    return tab[fmt] ? tab[fmt] : sp_big_rt;
 }
 static bool specialised(int fmt)
 {
@@ -107,6 +116,8 @@ struct sp_engine {
     DevBuf pin[2], pimg[2];                  // pipeline: double-buffered input bytes / image tiles
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_comp[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr }, ev_setup = nullptr;
+    DevBuf ring, ringctl;                    // n > 4096: L2-resident pre-pass ring and its queue / hand-off counters
+    size_t l2_window = 0;                    // bytes of the ring currently covered by the persisting access-policy window
     DevBuf in, zin, spec, image, fmin, fmax, fmid, gauges, hist, jhist, stats, mm, lut, window, window_t, scratch, db, synth_lut;
     // state of an enqueued (not yet finished) render
     std::vector<cudaEvent_t> prof0, prof1;   // per-launch timing ring of the render kernel
@@ -228,7 +239,7 @@ extern "C" void sp_destroy(sp_engine *e)
     for (auto &kv : e->twA) cudaFree(kv.second);
     for (auto &kv : e->twB) cudaFree(kv.second);
     DevBuf *bufs[] = { &e->in, &e->zin, &e->spec, &e->image, &e->fmin, &e->fmax, &e->fmid, &e->gauges, &e->hist, &e->jhist, &e->stats, &e->mm,
-                       &e->lut, &e->window, &e->window_t, &e->scratch, &e->db, &e->synth_lut, &e->pin[0], &e->pin[1],
+                       &e->lut, &e->window, &e->window_t, &e->ring, &e->ringctl, &e->scratch, &e->db, &e->synth_lut, &e->pin[0], &e->pin[1],
                        &e->pimg[0], &e->pimg[1] };
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (auto ev : e->prof0) cudaEventDestroy(ev);
@@ -287,6 +298,16 @@ static int get_twiddles(sp_engine *e, int n, const float2 **out)
     std::vector<float2> h((size_t)n);
     for (int i = 0; i < n; i++) h[i] = twid(i, n);
     return upload_table(e, e->tw, n, h, out);
+}
+// pre-pass twiddles of render_big_kernel: [R - 1][4096] = W_n^{j*k}, k = 1 .. R-1, j fastest (coalesced loads)
+static int get_big_twiddles(sp_engine *e, int n, const float2 **out)
+{
+    auto it = e->tw.find(-n);
+    if (it != e->tw.end()) { *out = it->second; return SP_OK; }
+    const int R = n / 4096;
+    std::vector<float2> h((size_t)(R - 1) * 4096);
+    for (int k = 1; k < R; k++) for (int j = 0; j < 4096; j++) h[(size_t)(k - 1) * 4096 + j] = twid((long long)j * k, n);
+    return upload_table(e, e->tw, -n, h, out);
 }
 // pass-A table [15][T]: W_N^{t*k}; pass-B table [15][RL]: W_{N/16}^{b*k}  (k = 1..15)
 static int get_pass_tables(sp_engine *e, int log2k, const float2 **twA, const float2 **twB)
@@ -676,6 +697,93 @@ static int launch_r64_kernel(sp_engine *e, r64_fn fn, Params &q, long long *nfas
     return SP_OK;
 }
 
+// n = R * 4096: frames [0, *nfast) (whole blocks of 8 frames inside the buffer) go through ONE launch of render_big_kernel, whose
+// pre-pass output lives in an L2-resident ring of S blocks (S * 8 * n * 8 bytes, pinned by a persisting access-policy window).
+static int launch_big_kernel(sp_engine *e, big_fn fn, Params &q, long long *nfast)
+{
+    const int n = q.n_full, R = q.sub_r;
+    long long nf = q.chunk_frames / 8 * 8;
+    const long long sw = sp::sample_width(q.format);
+    auto inside = [&](long long xr) {
+        const long long xgl = q.frame_first + q.chunk_first + xr;
+        const long long p0 = (long long)(0.5 + q.stride * (double)xgl) - q.sample_base;       // lib/worker.js:72
+        return p0 >= 0 && (unsigned long long)(p0 + n) * (unsigned long long)sw <= q.valid_bytes;
+    };
+    while (nf > 0 && !inside(nf - 1)) nf -= 8;
+    if (nf > 0 && !inside(0)) nf = 0;
+    *nfast = nf;
+    if (nf == 0) return SP_OK;
+    int occ = 0, rc;
+    sp::BigArgs g;
+    memset(&g, 0, sizeof g);
+    CU(fn(&q, &g, 0, e->stream, nullptr, &occ));
+    if (occ < 1) { *nfast = 0; return SP_OK; }
+    const int env_slots = getenv("SP_BIG_SLOTS") ? atoi(getenv("SP_BIG_SLOTS")) : 0;       // tuning / tests: ring slots and pre-pass lead
+    const int env_lead = getenv("SP_BIG_LEAD") ? atoi(getenv("SP_BIG_LEAD")) : 0;
+    // Ring: 80 MB of the 126 MB L2 (every CTA holds 512 KB of it for the length of a second-stage tile, so a smaller ring
+    // makes the pre-pass wait for free slots and a larger one spills to HBM - profiles/r02_big_kernel.txt), at least 8 blocks;
+    // the pre-pass runs L = 0.4 S blocks ahead of the second stage.
+    const size_t block_bytes = (size_t)8 * (size_t)n * 8;
+    int S = env_slots > 0 ? env_slots : (int)(((size_t)80 << 20) / block_bytes);
+    if (S < 8 && env_slots <= 0) S = 8;
+    if (S < 2) S = 2;
+    if (S > 64) S = 64;
+    int L = env_lead > 0 ? env_lead : (2 * S / 5 > 2 ? 2 * S / 5 : 2);
+    if (L > S) L = S;
+    if (L < 1) L = 1;
+    const float2 *tw14 = nullptr, *twT = nullptr;
+    if ((rc = get_r64_table(e, &tw14)) || (rc = get_big_twiddles(e, n, &twT))) return rc;
+    if ((rc = ensure(e, e->ring, (size_t)S * block_bytes)) || (rc = ensure(e, e->ringctl, 4 * (size_t)(1 + 2 * 64) + 64 + 64))) return rc;
+    if (e->l2_window != (size_t)S * block_bytes && !getenv("SP_BIG_NO_L2PIN")) {
+        // keep the ring in L2: persisting lines for the ring's address range, everything else streams through the rest
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, e->dev));
+        size_t want = (size_t)S * block_bytes;
+        if (prop.persistingL2CacheMaxSize > 0) {
+            const size_t set_aside = want < (size_t)prop.persistingL2CacheMaxSize ? want : (size_t)prop.persistingL2CacheMaxSize;
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside);
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof av);
+            av.accessPolicyWindow.base_ptr = e->ring.p;
+            av.accessPolicyWindow.num_bytes = want < (size_t)prop.accessPolicyMaxWindowSize ? want : (size_t)prop.accessPolicyMaxWindowSize;
+            av.accessPolicyWindow.hitRatio = 1.0f;
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+            cudaGetLastError();                               // best effort: the kernel is correct without the pin
+        }
+        e->l2_window = want;
+    }
+    CU(cudaMemsetAsync(e->ringctl.p, 0, 4 * (size_t)(1 + 2 * 64), e->stream));
+    g.ring = (float2 *)e->ring.p;
+    g.twT = twT;
+    g.ctl = (unsigned *)e->ringctl.p;
+    g.slots = S;
+    g.lead = L;
+    g.nblocks = nf / 8;
+    g.R = R;
+    g.dbg = getenv("SP_BIG_DBG") ? atoi(getenv("SP_BIG_DBG")) : 0;
+    // SP_BIG_STATS=1: per-phase SM cycle sums of the launch (development), printed when the engine is destroyed / next launch
+    static const bool want_stats = getenv("SP_BIG_STATS") != nullptr;
+    if (want_stats) {
+        g.stats = (unsigned long long *)((unsigned char *)e->ringctl.p + ((4 * (size_t)(1 + 2 * 64) + 63) & ~(size_t)63));
+        unsigned long long h[8];
+        CU(cudaMemcpyAsync(h, g.stats, sizeof h, cudaMemcpyDeviceToHost, e->stream));   // the PREVIOUS launch's sums (stream order)
+        CU(cudaStreamSynchronize(e->stream));
+        if (h[4] || h[5])
+            fprintf(stderr, "[big] P: %llu items, wait %.0f work %.0f (first frame landed after %.0f, 8-frame loop %.0f) cycles/item | F: %llu tiles, wait %.0f work %.0f cycles/tile\n", h[4],
+                    h[4] ? (double)h[0] / h[4] : 0.0, h[4] ? (double)h[1] / h[4] : 0.0, h[4] ? (double)h[6] / h[4] : 0.0, h[4] ? (double)h[7] / h[4] : 0.0, h[5], h[5] ? (double)h[2] / h[5] : 0.0, h[5] ? (double)h[3] / h[5] : 0.0);
+        CU(cudaMemsetAsync(g.stats, 0, 64, e->stream));
+    }
+    Params r = q;
+    r.chunk_frames = nf;
+    prof_begin(e);
+    CU(fn(&r, &g, e->sm_count, e->stream, tw14, nullptr));
+    prof_end(e);
+    e->launches += 2;
+    return SP_OK;
+}
+
 // Frames [0, *nfast) of the chunk go through render_rc_kernel (N = 256 .. 2048): whole tiles of 65536 / N frames inside the buffer.
 static int launch_rc_kernel(sp_engine *e, rc_fn fn, int log2n, Params &q, long long *nfast)
 {
@@ -784,7 +892,14 @@ static int enqueue_frames(sp_engine *e, Job &j, Params &p)
         const long long nf = p.nframes;
         sp::init_minmax_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, e->stream>>>((unsigned *)p.fmin, (unsigned *)p.fmax, nf);
         e->launches++;
-        for (long long c0 = 0; c0 < nf; c0 += ch) {
+        long long big_done = 0;
+        // SP_FOURSTEP=hbm selects the round-1 form (pre-pass kernel -> 1 GB scratch in HBM -> second-stage kernel) for A/B runs
+        static const bool hbm_scratch = getenv("SP_NO_BIG") || (getenv("SP_FOURSTEP") && !strcmp(getenv("SP_FOURSTEP"), "hbm"));
+        if (!tap && fused_eligible(p) && big_for(fmt) && !hbm_scratch) {
+            Params q = p;
+            if ((rc = launch_big_kernel(e, big_for(fmt), q, &big_done))) return rc;
+        }
+        for (long long c0 = big_done; c0 < nf; c0 += ch) {
             Params q = p;
             q.chunk_first = c0;
             q.chunk_frames = (nf - c0 < ch) ? nf - c0 : ch;

@@ -6,6 +6,7 @@
 #include "sp_kernels.cuh"
 #include "sp_kernel_r64.cuh"
 #include "sp_kernel_rc.cuh"
+#include "sp_kernel_big.cuh"
 
 namespace sp {
 
@@ -141,6 +142,28 @@ static cudaError_t launch_rc_v(const Params &p, int grid, cudaStream_t st, const
     }
 }
 
+// n = R * 4096 in one persistent launch (sp_kernel_big.cuh)
+template <int FMT>
+static cudaError_t launch_big_v(const Params &p, const BigArgs &g, int grid, cudaStream_t st, const float2 *tw14, int *occ_out)
+{
+    auto kfn = render_big_kernel<FMT>;
+    static bool attr_flags[64] = {};
+    bool &attr_done = attr_flag(attr_flags);
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BigCfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    if (occ_out) {
+        int nb = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, BigCfg::THREADS, BigCfg::SMEM_BYTES);
+        *occ_out = nb;
+        return e;
+    }
+    kfn<<<grid, BigCfg::THREADS, BigCfg::SMEM_BYTES, st>>>(p, g, tw14);
+    return cudaGetLastError();
+}
+
 } // namespace sp
 
 #define SP_CAT2(a, b) a##b
@@ -168,6 +191,10 @@ extern "C" cudaError_t SP_CAT(sp_rc_, SP_INST_TAG)(int log2n, const sp::Params *
     case 11: return sp::launch_rc_v<5, SP_INST_FMT>(*p, grid, st, tw14, occ_out);
     default: return cudaErrorInvalidValue;
     }
+}
+extern "C" cudaError_t SP_CAT(sp_big_, SP_INST_TAG)(const sp::Params *p, const sp::BigArgs *g, int grid, cudaStream_t st, const float2 *tw14, int *occ_out)
+{
+    return sp::launch_big_v<SP_INST_FMT>(*p, *g, grid, st, tw14, occ_out);
 }
 extern "C" cudaError_t SP_CAT(sp_pl_, SP_INST_TAG)(int r, const sp::Params *p, float2 *out, const float2 *tw_full,
                                                     cudaStream_t st)

@@ -257,6 +257,20 @@ def test_degenerate_messages_are_answered_like_the_reference(engine, fmt, n, wid
     run_both(engine, raw, fmt, n, width, "hann" if n > 2 else "rectangular", want_db=False)
 
 
+@pytest.mark.parametrize("n,width,slots,lead", [(8192, 200, 4, 2), (8192, 136, 4, 4), (16384, 96, 5, 1), (65536, 40, 4, 2), (32768, 67, 0, 0)])
+def test_big_kernel_ring_wraps(engine, monkeypatch, n, width, slots, lead):
+    """render_big_kernel with a ring of only 4-5 blocks: every slot is reused several times (P waits for the F items of the
+    slot's previous block, F for the 32 P items of its own), overlapping hops, the < 8-frame remainder on the generic path."""
+    if slots:
+        monkeypatch.setenv("SP_BIG_SLOTS", str(slots))
+        monkeypatch.setenv("SP_BIG_LEAD", str(lead))
+    S = int(n * (width - 1) * 0.37) + n + 11
+    raw = O.synth("CS16", 0, S, S, 99 + n).tobytes()
+    gpu, ora, nbad = run_both(engine, raw, "CS16", n, width, "hann", want_db=False)
+    g2 = engine.render(raw, "CS16", n, width, *O.window("hann", n)[:1], 1 / O.window("hann", n)[1], 6, 30, CM256)
+    assert np.array_equal(g2["image"], gpu["image"]) and np.array_equal(g2["cB_hist"], gpu["cB_hist"])     # repeatable
+
+
 @pytest.mark.parametrize("n,width", [(131072, 8), (262144, 4)])
 def test_sizes_above_65536(engine, n, width):
     """lib/fft_nayuki.js:38-39 accepts any power of two; the four-step path covers n up to 262144 (pre-pass radix 32 / 64)."""

@@ -41,7 +41,11 @@ def main():
         cases.append(("C4", fmt, 1024, 1, "hann", "viridis", 1 << 26))
     cases.append(("C5", "CF32", 65536, 1, "hann", "viridis", 1 << 28))
     pk = peak()
-    only = sys.argv[1].split(",") if len(sys.argv) > 1 else None      # e.g. "C5,C3-z1"
+    only = sys.argv[1].split(",") if len(sys.argv) > 1 else None      # e.g. "C5,C3-z1", or ad-hoc cases "X:CS16:65536:1:28" (format, n, zoom, log2 samples)
+    for spec in (only or []):
+        if spec.startswith("X:"):
+            _, f_, n_, z_, l_ = spec.split(":")
+            cases.append((spec, f_, int(n_), int(z_), "hann", "viridis", 1 << int(l_)))
     if len(sys.argv) > 2:
         steps = int(sys.argv[2])
     for tag, fmt, n, z, win, cmname, S in cases:
