@@ -1075,7 +1075,11 @@ static int render_pipelined(sp_engine *e, const sp_request *rq, sp_reply *rp, Jo
         s0 -= s0 % 16;
         if (s0 < buf_first) s0 = buf_first;
         unsigned long long b0 = (unsigned long long)(s0 - buf_first) * sw, b1 = (unsigned long long)(s1 - buf_first) * sw;
-        if (b1 > rq->byte_length || c == nchunks - 1) b1 = rq->byte_length;  // ragged tail bytes travel with the last chunk
+        // The chunk takes the samples its frames read and nothing more: a shard's buffer may extend past its frames (a caller may
+        // pass the whole capture with a frame sub-range).  The ragged tail (< 1 sample, or whatever lies between the last frame
+        // and the end of the capture) travels only with the chunk that holds the message's last global frame.
+        const bool msg_last = c == nchunks - 1 && (!shard || g_first + W == rq->total_width);
+        if (b1 > rq->byte_length || msg_last) b1 = rq->byte_length;
         if (b0 > b1) b0 = b1;
         if (b1 - b0 + 16 > in_cap) return fail(e, SP_E_RANGE, "internal: pipeline chunk larger than its buffer");
         // input buffer b is free once the render of chunk c-2 is done

@@ -38,9 +38,11 @@ class GpuWorker {
         if (!(msg && msg.buffer)) return // lib/worker.js:159 (also swallows the {transferable} probe)
         let data
         try {
-            const cmap = new Uint8Array(msg.cmap.length * 3)
-            msg.cmap.forEach((c, i) => { // Uint8ClampedArray store semantics for the table entries
-                for (let k = 0; k < 3; k++) cmap[3 * i + k] = Math.max(0, Math.min(255, Math.round(c[k]) || 0))
+            // the reference stores the table entries into a Uint8ClampedArray (lib/worker.js:118-120): clamp to [0, 255],
+            // round half to EVEN, NaN -> 0 - exactly what a Uint8ClampedArray store does, so let one do it
+            const cmap = new Uint8ClampedArray(msg.cmap.length * 3)
+            msg.cmap.forEach((c, i) => {
+                for (let k = 0; k < 3; k++) cmap[3 * i + k] = c[k]
             })
             const r = addon.render(this.engine, {
                 buffer: msg.buffer, format: formatId(msg.format), n: msg.n, width: msg.width,

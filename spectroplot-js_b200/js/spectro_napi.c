@@ -96,10 +96,17 @@ static napi_value Render(napi_env env, napi_callback_info info)
     napi_typedarray_type tt; napi_value ab; size_t off;
     napi_get_named_property(env, ctx, "windowc", &v);
     NAPI_OK(napi_get_typedarray_info(env, v, &tt, &len, &p, &ab, &off));       /* Float64Array(n) */
+    if (tt != napi_float64_array) { napi_throw_type_error(env, NULL, "windowc must be a Float64Array"); return NULL; }
+    if (rq.n < SP_MIN_N || rq.n > SP_MAX_N || (rq.n & (rq.n - 1))) { napi_throw_range_error(env, NULL, "Length is not a power of 2"); return NULL; }
+    if (len < (size_t)rq.n) { napi_throw_range_error(env, NULL, "windowc is shorter than n"); return NULL; }   /* sp_render reads n doubles */
     rq.windowc = (const double *)p;
     napi_get_named_property(env, ctx, "cmap", &v);
-    NAPI_OK(napi_get_typedarray_info(env, v, &tt, &len, &p, &ab, &off));       /* Uint8Array(len*3) */
+    NAPI_OK(napi_get_typedarray_info(env, v, &tt, &len, &p, &ab, &off));       /* Uint8Array / Uint8ClampedArray(len*3) */
+    if (tt != napi_uint8_array && tt != napi_uint8_clamped_array) { napi_throw_type_error(env, NULL, "cmap must be a Uint8Array or Uint8ClampedArray"); return NULL; }
+    if (len % 3 != 0 || len < 6 || len > 3 * (size_t)SP_MAX_CMAP) { napi_throw_range_error(env, NULL, "cmap must hold 2 .. 4096 RGB triples"); return NULL; }
     rq.cmap_rgb = (const uint8_t *)p; rq.cmap_len = (int32_t)(len / 3);
+    /* the outputs below are sized from width and n: range-check them before allocating (sp_render validates the rest) */
+    if (rq.width < 1 || (double)rq.width * (double)rq.n > 17179869184.0) { napi_throw_range_error(env, NULL, "width out of range"); return NULL; }
     rq.channel_mode = get_bool(env, ctx, "channelMode");
     rq.waterfall = get_bool(env, ctx, "waterfall");
 

@@ -139,26 +139,26 @@ function createSpectroplot(deps) {
         }
 
         zoomOut() { // :513-527: half steps inside [1, 8]
-            if (this.zoom <= 1) return undefined
+            if (this.zoom <= 1) return Promise.resolve()
             this.zoom -= 0.5
             return this.processData()
         }
 
         zoomFit() {
-            if (this.zoom == 1) return undefined
+            if (this.zoom == 1) return Promise.resolve()
             this.zoom = 1
             return this.processData()
         }
 
         zoomIn() {
-            if (this.zoom >= 8) return undefined
+            if (this.zoom >= 8) return Promise.resolve()
             this.zoom += 0.5
             return this.processData()
         }
 
         // lib/spectroplot.js:1096-1285 without the drawing: build one message per worker, merge the replies
         processData() {
-            if (!this.buffer || !this.sampleView || !this.sampleView.buffer) return undefined
+            if (!this.buffer || !this.sampleView || !this.sampleView.buffer) return Promise.resolve() // :1097-1098
             if (this.inProcess) return this.inProcess // single flight: a second request is dropped (:1099)
 
             const waterfall = !!this.turnFlip

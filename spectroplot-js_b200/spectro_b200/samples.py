@@ -3,6 +3,8 @@
 Only the host-side bookkeeping lives here (format aliases, bytes per sample, sampleCount,
 slice); decoding itself runs on the GPU (csrc/sp_device.cuh).
 """
+import numpy as np
+
 from . import _lib
 
 # format -> (sampleWidth bytes, typed-array element bytes)   lib/samples.js:30-139
@@ -46,7 +48,12 @@ class SampleView:
             self.buffer = data.tobytes()
             self.sampleCount = len(data) // 2
             return self
-        buffer = bytes(buffer) if not isinstance(buffer, (bytes, bytearray, memoryview)) else buffer
+        # zero copy for anything that exposes the buffer protocol: a page-locked numpy array from ingest.load_capture() stays
+        # page-locked (slices are views), so Engine.make_request hands the pinned pointer to the pipelined host path
+        if isinstance(buffer, np.ndarray):
+            buffer = np.ascontiguousarray(buffer).view(np.uint8).reshape(-1)
+        elif not isinstance(buffer, (bytes, bytearray, memoryview)):
+            buffer = memoryview(buffer).cast("B")
         if len(buffer) % self.elementSize:
             raise ValueError("RangeError: byte length of typed array should be a multiple of %d" % self.elementSize)
         self.buffer = buffer

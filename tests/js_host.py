@@ -42,7 +42,7 @@ def make_addon(I, render_fn, log):
         assert isinstance(buf, JSArrayBuffer), "ctx.buffer must be an ArrayBuffer (napi_get_arraybuffer_info)"
         wc, cm = g("windowc"), g("cmap")
         assert isinstance(wc, JSTypedArray) and wc.kind == "Float64Array", "ctx.windowc must be a Float64Array"
-        assert isinstance(cm, JSTypedArray) and cm.kind == "Uint8Array", "ctx.cmap must be a Uint8Array(len*3)"
+        assert isinstance(cm, JSTypedArray) and cm.kind in ("Uint8Array", "Uint8ClampedArray"), "ctx.cmap must be a Uint8Array or Uint8ClampedArray(len*3)"
         n, width = int(g("n")), int(g("width"))
         log.append(("render", FORMATS[int(g("format"))], n, width))
         try:

@@ -69,6 +69,8 @@ napi_status napi_throw_error(napi_env env, const char *code, const char *msg)
     env->pending = 1;
     return napi_ok;
 }
+napi_status napi_throw_type_error(napi_env env, const char *code, const char *msg) { return napi_throw_error(env, code, msg); }
+napi_status napi_throw_range_error(napi_env env, const char *code, const char *msg) { return napi_throw_error(env, code, msg); }
 napi_status napi_create_external(napi_env env, void *data, napi_finalize f, void *hint, napi_value *r) { (void)env; (void)f; (void)hint; napi_value v = nv(K_EXT); v->data = data; *r = v; return napi_ok; }
 napi_status napi_get_value_external(napi_env env, napi_value v, void **r) { (void)env; if (!v || v->kind != K_EXT) return napi_invalid_arg; *r = v->data; return napi_ok; }
 napi_status napi_get_arraybuffer_info(napi_env env, napi_value v, void **data, size_t *len)

@@ -40,6 +40,8 @@ napi_status napi_get_value_bool(napi_env env, napi_value value, bool *result);
 napi_status napi_coerce_to_bool(napi_env env, napi_value value, napi_value *result);
 napi_status napi_get_cb_info(napi_env env, napi_callback_info cbinfo, size_t *argc, napi_value *argv, napi_value *this_arg, void **data);
 napi_status napi_throw_error(napi_env env, const char *code, const char *msg);
+napi_status napi_throw_type_error(napi_env env, const char *code, const char *msg);
+napi_status napi_throw_range_error(napi_env env, const char *code, const char *msg);
 napi_status napi_create_external(napi_env env, void *data, napi_finalize finalize_cb, void *finalize_hint, napi_value *result);
 napi_status napi_get_value_external(napi_env env, napi_value value, void **result);
 napi_status napi_get_arraybuffer_info(napi_env env, napi_value arraybuffer, void **data, size_t *byte_length);

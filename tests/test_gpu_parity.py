@@ -633,6 +633,25 @@ def test_multi_device_engine_equals_single_device(engine):
         multi.close()
 
 
+def test_pipelined_shard_with_an_oversized_buffer(engine, monkeypatch):
+    """A frame-range shard whose host buffer is the WHOLE capture (buffer_first_sample = 0) on the pipelined path: each chunk
+    must take only the samples its frames read - the last chunk used to span to the end of the buffer and trip the
+    staging-buffer check with SP_E_RANGE."""
+    import spectro_b200
+    monkeypatch.setenv("SP_PIPE_MB", "1")
+    fmt, n, W = "CS16", 1024, 4096
+    S = n * W // 2 + 7
+    buf = O.synth(fmt, 0, S, S, 4242).tobytes()
+    w, wt = O.window("hann", n)
+    whole = engine.render(buf, fmt, n, W, w, 1 / wt, 6, 30, CM256)
+    x0, x1 = 512, 2048                                   # a sub-range well inside: its frames end far before the buffer does
+    shard = dict(total_byte_length=len(buf), total_width=W, frame_first=x0, buffer_first_sample=0)
+    part = engine.render(buf, fmt, n, x1 - x0, w, 1 / wt, 6, 30, CM256, shard=shard)
+    assert np.array_equal(part["image"], whole["image"][:, x0:x1])
+    for k in ("gauge_mins", "gauge_maxs", "gauge_amps"):
+        assert np.array_equal(part[k], whole[k][x0:x1]), k
+
+
 @pytest.mark.parametrize("fmt,n,width", [("CS16", 4096, 40), ("CS16", 4096, 21), ("CF32", 4096, 64), ("CU8", 1024, 200), ("CS16", 2048, 37),
                                          ("CF32", 512, 136), ("CS4", 256, 300)])
 def test_waterfall_on_the_fused_kernels(engine, fmt, n, width):

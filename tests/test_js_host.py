@@ -133,7 +133,8 @@ def test_headless_spectroplot_js_matches_reference_fanout():
     g = lambda k: I.get_prop(sp, k)
     call = lambda name, *a: I.call(g(name), sp, list(a))
     assert [t for t in host.log] == [("create", 0)] * 3
-    assert call("setOption", "fftN", 512) is UNDEF               # no data yet: nothing to render (:1097)
+    # no data yet: nothing to render, but a drop-in caller's `.then` must still work (lib/spectroplot.js:1097: Promise.resolve())
+    assert host.await_(call("setOption", "fftN", 512)) is UNDEF
     assert g("fftN") == 512
     S = 30000
     buf = O.synth("CS16", 0, S, S, 9).tobytes()
@@ -164,7 +165,7 @@ def test_headless_spectroplot_js_matches_reference_fanout():
     assert I.get_prop(r1, "width") == width
     assert g("inProcess") is False
     # zoom: half steps inside [1, 8] (:513-527); waterfall via turnFlip
-    assert call("zoomOut") is UNDEF
+    assert host.await_(call("zoomOut")) is UNDEF               # already at zoom 1: Promise.resolve() (:514)
     r2 = host.await_(call("zoomIn"))
     assert g("zoom") == 1.5 and I.get_prop(r2, "width") == int(500 * 1.5 - 200)
     r3 = host.await_(call("setOptions", I.from_py({"turnFlip": "flip", "zoom": "1", "fftN": "128"})))

@@ -134,6 +134,14 @@ def test_addon_render_matches_reference_replies(fk):
     # a windowc that is not a typed array is refused by napi_get_typedarray_info, not read as garbage
     with pytest.raises(RuntimeError, match="napi_get_typedarray_info"):
         a.call("render", eng, a.ctx(f, windowc=a.ab(f["windowc"].tobytes())))
+    # windowc of the wrong element type or shorter than n would be read out of bounds on the JS heap: refused
+    F32 = 7
+    with pytest.raises(RuntimeError, match="Float64Array"):
+        a.call("render", eng, a.ctx(f, windowc=fk.fk_typedarray(F32, a.ab(f["windowc"].astype(np.float32).tobytes()), 0, int(f["n"]))))
+    with pytest.raises(RuntimeError, match="shorter than n"):
+        a.call("render", eng, a.ctx(f, windowc=a.ta(F64, f["windowc"].astype(np.float64)[: int(f["n"]) // 2])))
+    with pytest.raises(RuntimeError, match="width out of range"):
+        a.call("render", eng, a.ctx(f, width=0))
     a.call("destroy", eng)
     # create([devices]): one engine over several GPUs (sp_create with ndev > 1); with one GPU in the box a one-element list
     import torch
