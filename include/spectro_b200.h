@@ -71,7 +71,9 @@ enum sp_error {
     SP_E_NO_DEVICE = -9,    /* no usable sm_100 device: there is NO CPU fallback       */
     SP_E_RANGE = -10,       /* shard fields inconsistent with the global message       */
     SP_E_ALIGN = -11,       /* device-resident buffer not 16-byte aligned              */
-    SP_E_NCCL = -12         /* multi-device merge failed                               */
+    SP_E_NCCL = -12         /* sp_render_shards: NCCL could not be loaded / initialised
+                               (libnccl.so.2 is opened with dlopen when a multi-device engine
+                               is created), or the merge collective failed               */
 };
 
 #define SP_MIN_N 2          /* reference accepts any power of two (lib/fft_nayuki.js:38-39); kernels cover
@@ -160,9 +162,11 @@ int sp_element_size(int format);   /* typed-array element size in bytes         
  * straight into the caller's image; the histograms and min / max are merged on
  * the host like lib/spectroplot.js:1229-1238 (ndev x ~10 KB).  The result is
  * the single-device result (bit-identical when the width is a multiple of 8).
- * The other entry points (taps, memory helpers, sp_render_enqueue) address the
- * first device; one process per GPU with an NCCL merge is the alternative
- * layout (bench.py).  Fails with SP_E_NO_DEVICE when no sm_100 GPU is present. */
+ * Device-resident shards are rendered and merged over NVLink by
+ * sp_render_shards() (one NCCL communicator per device, ncclCommInitAll at
+ * creation; libnccl is opened with dlopen, so a single-GPU host needs none).
+ * The taps and memory helpers address the device chosen with sp_select_device().
+ * Fails with SP_E_NO_DEVICE when no sm_100 GPU is present. */
 int sp_create(sp_engine **out, const int *device_ids, int ndev);
 void sp_destroy(sp_engine *e);
 const char *sp_last_error(sp_engine *e); /* e may be NULL: last error of sp_create */
@@ -179,6 +183,18 @@ int sp_render(sp_engine *e, const sp_request *rq, sp_reply *rp);
  * with sp_render_finish().  Used to time the kernels without a host sync. */
 int sp_render_enqueue(sp_engine *e, const sp_request *rq, sp_reply *rp);
 int sp_render_finish(sp_engine *e, sp_reply *rp);
+
+/* Device-resident shards of ONE message on a multi-device engine: rq[g] / rp[g] (g = 0 .. ndev-1) describe the
+ * frame-range shard that lives on device g - bytes, image band, gauges, both histograms and minmax_dev are device
+ * pointers on THAT device (SP_F_BUFFER_ON_DEVICE | SP_F_REPLY_ON_DEVICE, shard fields set; allocate with
+ * sp_select_device + sp_device_alloc).  Every device renders its shard on its own stream, then one grouped NCCL
+ * all-reduce over NVLink merges cB_hist / c_hist (sum, u64) and {dBfs_min, dBfs_max} (min / max, f64) in place:
+ * the caller-side merge of lib/spectroplot.js:1229-1238 without a host copy.  On return every reply carries the
+ * statistics of the WHOLE message; the image bands and gauges stay per device.  SP_E_NCCL when NCCL is missing. */
+int sp_render_shards(sp_engine *e, const sp_request *rq, sp_reply *rp);
+
+/* Which device of a multi-device engine the taps, the memory helpers and sp_synth_fill address (default 0). */
+int sp_select_device(sp_engine *e, int index);
 
 /* Several zoom levels of ONE capture in one pass over the capture bytes: the buffer crosses PCIe
  * once (or is bound, if device-resident) and level i is rendered as the message `rq` with

@@ -10,6 +10,7 @@
 #include "sp_kernel_w.cuh"
 
 #include <cmath>
+#include <dlfcn.h>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -102,6 +103,46 @@ extern "C" const char *sp_format_name(int f) { return (f < 0 || f >= SP_FORMAT_C
 extern "C" int sp_sample_width(int f) { return (f < 0 || f >= SP_FORMAT_COUNT) ? SP_E_BAD_FORMAT : sp::sample_width(f); }
 extern "C" int sp_element_size(int f) { return (f < 0 || f >= SP_FORMAT_COUNT) ? SP_E_BAD_FORMAT : sp::element_size(f); }
 
+// ------------------------------------------------------------------ NCCL, loaded at run time
+// Only a multi-device engine needs it (the merge of lib/spectroplot.js:1229-1238 across GPUs), so the library is opened with
+// dlopen when such an engine is created: a single-GPU host needs no NCCL installation, and the .so keeps linking the CUDA
+// runtime only.  The handful of types below are NCCL's stable C ABI (nccl.h).
+typedef struct ncclComm *sp_ncclComm_t;
+enum { SP_NCCL_UINT64 = 5, SP_NCCL_FLOAT64 = 8, SP_NCCL_SUM = 0, SP_NCCL_MAX = 2, SP_NCCL_MIN = 3 };
+struct NcclApi {
+    void *lib = nullptr;
+    int (*CommInitAll)(sp_ncclComm_t *, int, const int *) = nullptr;
+    int (*CommDestroy)(sp_ncclComm_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, sp_ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::string err;
+};
+static NcclApi *nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return &api;
+    tried = true;
+    const char *names[] = { getenv("SP_NCCL_LIB"), "libnccl.so.2", "libnccl.so" };
+    for (const char *nm : names) {
+        if (!nm || !*nm) continue;
+        api.lib = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) { api.err = std::string("dlopen(libnccl.so.2): ") + (dlerror() ? dlerror() : "not found"); return &api; }
+    auto sym = [&](const char *s) { void *f = dlsym(api.lib, s); if (!f && api.err.empty()) api.err = std::string("missing symbol ") + s; return f; };
+    api.CommInitAll = (int (*)(sp_ncclComm_t *, int, const int *))sym("ncclCommInitAll");
+    api.CommDestroy = (int (*)(sp_ncclComm_t))sym("ncclCommDestroy");
+    api.AllReduce = (int (*)(const void *, void *, size_t, int, int, sp_ncclComm_t, cudaStream_t))sym("ncclAllReduce");
+    api.GroupStart = (int (*)())sym("ncclGroupStart");
+    api.GroupEnd = (int (*)())sym("ncclGroupEnd");
+    api.GetErrorString = (const char *(*)(int))sym("ncclGetErrorString");
+    if (!api.err.empty()) { dlclose(api.lib); api.lib = nullptr; }
+    return &api;
+}
+
 // ------------------------------------------------------------------ engine state
 struct DevBuf {
     void *p = nullptr;
@@ -113,6 +154,9 @@ struct Placement { long long pitch_frames; long long col0; };
 
 struct sp_engine {
     std::vector<sp_engine *> subs;           // ndev > 1: one single-device engine per GPU; this object only dispatches
+    std::vector<sp_ncclComm_t> comms;        // ndev > 1: one NCCL communicator per device (ncclCommInitAll), empty when NCCL is unavailable
+    std::string nccl_err;                    // why `comms` is empty
+    int cur = 0;                             // sub-engine addressed by the memory helpers / taps (sp_select_device)
     int ndev = 1;
     int dev = 0;
     int sm_count = 0;
@@ -172,14 +216,14 @@ static int ensure(sp_engine *e, DevBuf &b, size_t bytes)
 // entry points other than sp_render work on the first device of a multi-device engine (taps, memory helpers, plan)
 static sp_engine *dev0(sp_engine *e)
 {
-    if (e && !e->subs.empty()) { e->err.clear(); return e->subs[0]; }
+    if (e && !e->subs.empty()) { e->err.clear(); return e->subs[(size_t)e->cur]; }
     return e;
 }
 
 extern "C" const char *sp_last_error(sp_engine *e)
 {
     if (!e) return g_create_err.c_str();
-    if (!e->subs.empty() && e->err.empty()) return e->subs[0]->err.c_str();
+    if (!e->subs.empty() && e->err.empty()) return e->subs[(size_t)e->cur]->err.c_str();
     return e->err.c_str();
 }
 
@@ -204,6 +248,20 @@ extern "C" int sp_create(sp_engine **out, const int *device_ids, int ndev)
         }
         parent->dev = parent->subs[0]->dev;
         parent->sm_count = parent->subs[0]->sm_count;
+        // one communicator per device for the merge of device-resident shards (sp_render_shards).  A host without NCCL still
+        // gets the engine: host-buffer messages are merged on the host, and sp_render_shards reports SP_E_NCCL.
+        NcclApi *nc = nccl_api();
+        if (!nc->lib) parent->nccl_err = nc->err;
+        else {
+            std::vector<int> devs;
+            for (sp_engine *s2 : parent->subs) devs.push_back(s2->dev);
+            parent->comms.assign((size_t)ndev, nullptr);
+            const int r = nc->CommInitAll(parent->comms.data(), ndev, devs.data());
+            if (r != 0) {
+                parent->nccl_err = std::string("ncclCommInitAll: ") + (nc->GetErrorString ? nc->GetErrorString(r) : "failed");
+                parent->comms.clear();
+            }
+        }
         *out = parent;
         return SP_OK;
     }
@@ -237,6 +295,8 @@ extern "C" void sp_destroy(sp_engine *e)
 {
     if (!e) return;
     if (!e->subs.empty()) {
+        for (size_t g = 0; g < e->comms.size(); g++)
+            if (e->comms[g]) { cudaSetDevice(e->subs[g]->dev); cudaDeviceSynchronize(); nccl_api()->CommDestroy(e->comms[g]); }
         for (sp_engine *sub : e->subs) sp_destroy(sub);
         delete e;
         return;
@@ -274,6 +334,13 @@ extern "C" int sp_set_stream(sp_engine *e, void *cuda_stream)
     return SP_OK;
 }
 extern "C" int sp_device_count(sp_engine *e) { return e ? e->ndev : 0; }
+extern "C" int sp_select_device(sp_engine *e, int index)
+{
+    if (!e) return SP_E_INVAL;
+    if (index < 0 || index >= e->ndev) return fail(e, SP_E_INVAL, "device index %d outside [0, %d)", index, e->ndev);
+    e->cur = index;
+    return SP_OK;
+}
 extern "C" int sp_sm_count(sp_engine *e) { return e ? e->sm_count : 0; }
 
 // ------------------------------------------------------------------ helpers
@@ -1139,7 +1206,7 @@ static int finish(sp_engine *e, sp_reply *rp)
 extern "C" int sp_render_enqueue(sp_engine *e, const sp_request *rq, sp_reply *rp)
 {
     if (!e || !rq || !rp) return fail(e, SP_E_INVAL, "null argument");
-    if (!e->subs.empty()) return fail(e, SP_E_INVAL, "sp_render_enqueue works on device-resident buffers: use one engine per GPU");
+    if (!e->subs.empty()) return fail(e, SP_E_INVAL, "sp_render_enqueue works on ONE device's buffers: use sp_render_shards on a multi-device engine");
     if (!(rq->flags & SP_F_BUFFER_ON_DEVICE) || !(rq->flags & SP_F_REPLY_ON_DEVICE))
         return fail(e, SP_E_INVAL, "sp_render_enqueue needs SP_F_BUFFER_ON_DEVICE | SP_F_REPLY_ON_DEVICE");
     Job j;
@@ -1158,6 +1225,59 @@ extern "C" int sp_render_finish(sp_engine *e, sp_reply *rp)
     e->pending = false;
     CU(cudaSetDevice(e->dev));
     return finish(e, rp);
+}
+
+
+// Device-resident shards of ONE message on a multi-device engine (lib/spectroplot.js:1206-1238 across GPUs, no host copy
+// of anything): shard g lives on device g (its bytes, its image band, its gauges, its two histograms and a double[2] for
+// min / max, all device pointers), the frame-range fields say which frames of the whole message it renders.  Every device
+// renders its shard on its own stream; then ONE grouped NCCL all-reduce per device merges the histograms (sum, u64) and
+// dBfs_min / dBfs_max (min / max, f64) in place over NVLink, so that every reply holds the statistics of the whole message.
+extern "C" int sp_render_shards(sp_engine *e, const sp_request *rqs, sp_reply *rps)
+{
+    if (!e || !rqs || !rps) return fail(e, SP_E_INVAL, "null argument");
+    if (e->subs.empty()) return fail(e, SP_E_INVAL, "sp_render_shards needs a multi-device engine (sp_create with ndev > 1)");
+    NcclApi *nc = nccl_api();
+    if (e->comms.empty()) return fail(e, SP_E_NCCL, "NCCL is not available: %s", e->nccl_err.c_str());
+    const int G = (int)e->subs.size();
+    for (int g = 0; g < G; g++) {
+        const sp_request &rq = rqs[g];
+        if (!(rq.flags & SP_F_BUFFER_ON_DEVICE) || !(rq.flags & SP_F_REPLY_ON_DEVICE))
+            return fail(e, SP_E_INVAL, "shard %d: sp_render_shards needs SP_F_BUFFER_ON_DEVICE | SP_F_REPLY_ON_DEVICE", g);
+        if (!rps[g].cB_hist || !rps[g].c_hist || !rps[g].minmax_dev)
+            return fail(e, SP_E_INVAL, "shard %d: cB_hist, c_hist and minmax_dev (device pointers) are the merge targets", g);
+        if (rq.cmap_len != rqs[0].cmap_len || rq.total_width != rqs[0].total_width || rq.total_width == 0)
+            return fail(e, SP_E_RANGE, "shard %d: the shards must describe the same message (total_width, cmap_len)", g);
+    }
+    for (int g = 0; g < G; g++) {
+        const int rc = sp_render_enqueue(e->subs[(size_t)g], &rqs[g], &rps[g]);
+        if (rc) {
+            e->err = "device " + std::to_string(e->subs[(size_t)g]->dev) + ": " + e->subs[(size_t)g]->err;
+            for (int k = 0; k < g; k++) { cudaSetDevice(e->subs[(size_t)k]->dev); cudaStreamSynchronize(e->subs[(size_t)k]->stream); e->subs[(size_t)k]->pending = false; }
+            return rc;
+        }
+    }
+    int r = nc->GroupStart();
+    for (int g = 0; g < G && r == 0; g++) {
+        sp_engine *s = e->subs[(size_t)g];
+        cudaSetDevice(s->dev);
+        if (r == 0) r = nc->AllReduce(rps[g].cB_hist, rps[g].cB_hist, SP_CB_HIST_SIZE, SP_NCCL_UINT64, SP_NCCL_SUM, e->comms[(size_t)g], s->stream);
+        if (r == 0) r = nc->AllReduce(rps[g].c_hist, rps[g].c_hist, (size_t)rqs[g].cmap_len, SP_NCCL_UINT64, SP_NCCL_SUM, e->comms[(size_t)g], s->stream);
+        if (r == 0) r = nc->AllReduce(rps[g].minmax_dev, rps[g].minmax_dev, 1, SP_NCCL_FLOAT64, SP_NCCL_MIN, e->comms[(size_t)g], s->stream);
+        if (r == 0) r = nc->AllReduce(rps[g].minmax_dev + 1, rps[g].minmax_dev + 1, 1, SP_NCCL_FLOAT64, SP_NCCL_MAX, e->comms[(size_t)g], s->stream);
+    }
+    const int r2 = nc->GroupEnd();
+    if (r == 0) r = r2;
+    int rc_out = SP_OK;
+    for (int g = 0; g < G; g++) {            // wait for render + merge on every device; dBfs_min / max of the WHOLE message
+        sp_engine *s = e->subs[(size_t)g];
+        s->pending = false;
+        cudaSetDevice(s->dev);
+        const int rc = finish(s, &rps[g]);
+        if (rc && !rc_out) { rc_out = rc; e->err = "device " + std::to_string(s->dev) + ": " + s->err; }
+    }
+    if (r != 0) return fail(e, SP_E_NCCL, "NCCL merge failed: %s", nc->GetErrorString ? nc->GetErrorString(r) : "error");
+    return rc_out;
 }
 
 static int render_one(sp_engine *e, const sp_request *rq, sp_reply *rp, const Placement *pl)

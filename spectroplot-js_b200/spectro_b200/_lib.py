@@ -33,7 +33,8 @@ SYMBOLS = ["sp_abi_version", "sp_format_from_name", "sp_format_name", "sp_sample
            "sp_create", "sp_destroy", "sp_last_error", "sp_set_stream", "sp_render", "sp_render_enqueue",
            "sp_render_finish", "sp_render_zooms", "sp_decode", "sp_render_db", "sp_device_alloc", "sp_device_free", "sp_memcpy_h2d",
            "sp_memcpy_d2h", "sp_host_alloc_pinned", "sp_host_free_pinned", "sp_device_sync", "sp_synth_fill",
-           "sp_synth_lut", "sp_device_count", "sp_sm_count", "sp_kernel_plan", "sp_profile_enable", "sp_profile_read"]
+           "sp_synth_lut", "sp_device_count", "sp_sm_count", "sp_kernel_plan", "sp_profile_enable", "sp_profile_read",
+           "sp_render_shards", "sp_select_device"]
 
 
 class SpError(RuntimeError):
@@ -84,6 +85,8 @@ def load():
     for fn in ("sp_render", "sp_render_enqueue"):
         getattr(lib, fn).argtypes = [C.c_void_p, C.POINTER(Request), C.POINTER(Reply)]
     lib.sp_render_finish.argtypes = [C.c_void_p, C.POINTER(Reply)]
+    lib.sp_render_shards.argtypes = [C.c_void_p, C.POINTER(Request), C.POINTER(Reply)]
+    lib.sp_select_device.argtypes = [C.c_void_p, C.c_int]
     lib.sp_render_db.argtypes = [C.c_void_p, C.POINTER(Request), C.c_void_p]
     lib.sp_render_zooms.argtypes = [C.c_void_p, C.POINTER(Request), C.c_int, C.POINTER(C.c_int64), C.POINTER(Reply)]
     lib.sp_decode.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
@@ -229,6 +232,22 @@ class Engine:
     def render_finish(self, rp: "Reply") -> "Reply":
         self._check(self.lib.sp_render_finish(self.h, C.byref(rp)))
         return rp
+
+    # ---- multi-device engine: device-resident shards, NCCL merge inside the C ABI
+    def select_device(self, index: int):
+        """Which device of a multi-device engine alloc / free / h2d / d2h / synth_fill address."""
+        self._check(self.lib.sp_select_device(self.h, int(index)))
+
+    def render_shards(self, requests, replies):
+        """sp_render_shards: requests[g] / replies[g] live on device g; every reply comes back with the merged histograms
+        (device) and dBfs_min / dBfs_max (host fields) of the whole message."""
+        n = len(self.devices)
+        assert len(requests) == n and len(replies) == n
+        rq, rp = (Request * n)(*requests), (Reply * n)(*replies)
+        for r in rq:
+            r.flags |= F_BUFFER_ON_DEVICE | F_REPLY_ON_DEVICE
+        self._check(self.lib.sp_render_shards(self.h, rq, rp))
+        return list(rp)
 
     # ---- taps
     def decode(self, fmt, buf, first: int = 0, count: int | None = None) -> np.ndarray:

@@ -4,6 +4,8 @@ properties at larger sizes.  Tolerances are BASELINE.json's (see helpers.py)."""
 import glob
 import os
 
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -631,6 +633,77 @@ def test_multi_device_engine_equals_single_device(engine):
         pin.free()
     finally:
         multi.close()
+
+
+@pytest.mark.parametrize("fmt,n,W", [("CS16", 4096, 256), ("CF32", 8192, 64), ("CU8", 512, 1000)])
+def test_render_shards_nccl_merge_equals_single_device(engine, fmt, n, W):
+    """sp_render_shards (C ABI, no torch): device-GENERATED shards on a multi-device engine, the histograms and min / max merged
+    by ONE grouped NCCL all-reduce on the engines' streams (lib/spectroplot.js:1229-1238 over NVLink) == the single-device
+    result.  Needs two GPUs (`gpurun --gpus 2`)."""
+    import torch
+    import spectro_b200
+    from spectro_b200 import sharding, _lib
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    G = 2
+    S = n * W // 2 + 5
+    sw = _lib.load().sp_sample_width(_lib.format_id(fmt))
+    w, wt = O.window("hann", n)
+    seed = 0xC5C5 + n
+    # single device: the whole message from a device-generated capture
+    d_all = engine.alloc(S * sw + 256)
+    engine.synth_fill(d_all, fmt, 0, S, S, seed)
+    host = np.empty(S * sw, np.uint8)
+    engine.d2h(host, d_all)
+    engine.free(d_all)
+    one = engine.render(host, fmt, n, W, w, 1 / wt, 6, 30, CM256)
+    multi = spectro_b200.Engine(list(range(G)))
+    try:
+        plan = sharding.plan_shards(S, n, W, G)
+        rqs, rps, bufs, keep = [], [], [], []
+        for g, sh in enumerate(plan):
+            multi.select_device(g)
+            nb = sh["sample_count"] * sw
+            d_in = multi.alloc(nb + 256)
+            multi.synth_fill(d_in, fmt, sh["sample_first"], sh["sample_count"], S, seed)      # generated on ITS device
+            d_img, d_g = multi.alloc(4 * sh["width"] * n), multi.alloc(3 * sh["width"])
+            d_hist, d_mm = multi.alloc(8 * (1000 + len(CM256))), multi.alloc(16)
+            rq, k = multi.make_request(d_in, fmt, n, sh["width"], w, 1 / wt, 6, 30, CM256, byte_length=nb,
+                                       shard=sharding.shard_fields(sh, S, sw, W))
+            keep.append(k)
+            p = lambda v: C.c_void_p(int(v))
+            rps.append(_lib.Reply(p(d_img), p(d_g), p(d_g + sh["width"]), p(d_g + 2 * sh["width"]), p(d_hist), p(d_hist + 8000),
+                                  0.0, 0.0, 0.0, 0, p(d_mm)))
+            rqs.append(rq)
+            bufs.append((d_in, d_img, d_g, d_hist, d_mm))
+        out = multi.render_shards(rqs, rps)
+        for g, sh in enumerate(plan):
+            multi.select_device(g)
+            d_in, d_img, d_g, d_hist, d_mm = bufs[g]
+            img = np.empty((n, sh["width"], 4), np.uint8)
+            multi.d2h(img, d_img)
+            assert np.array_equal(img, one["image"][:, sh["frame_first"]:sh["frame_first"] + sh["width"]]), g
+            hist = np.empty(1000 + len(CM256), np.uint64)
+            multi.d2h(hist, d_hist)
+            # EVERY device holds the histograms of the whole message after the all-reduce
+            assert np.array_equal(hist[:1000], one["cB_hist"]) and np.array_equal(hist[1000:], one["c_hist"]), g
+            assert out[g].dBfs_min == one["dBfs_min"] and out[g].dBfs_max == one["dBfs_max"], g
+            gg = np.empty(3 * sh["width"], np.uint8)
+            multi.d2h(gg, d_g)
+            assert np.array_equal(gg[:sh["width"]], one["gauge_mins"][sh["frame_first"]:sh["frame_first"] + sh["width"]])
+            for d in bufs[g]:
+                multi.free(d)
+    finally:
+        multi.close()
+
+
+def test_render_shards_needs_a_multi_device_engine(engine):
+    import spectro_b200
+    from spectro_b200 import _lib
+    rq = _lib.Request()
+    rp = _lib.Reply()
+    rc = engine.lib.sp_render_shards(engine.h, C.byref(rq), C.byref(rp))
+    assert _lib.ERRORS[rc] == "SP_E_INVAL" and b"multi-device" in engine.lib.sp_last_error(engine.h)
 
 
 def test_pipelined_shard_with_an_oversized_buffer(engine, monkeypatch):
