@@ -13,7 +13,12 @@ stride and the histograms / min / max are merged with NCCL all-reduces (no data-
 
 Prints ONE JSON line (rank 0).  `value` = device-resident input -> device-resident outputs;
 `e2e` = the same through the public host-buffer API (pinned host input -> pinned host outputs,
-H2D and D2H inside the timed region).
+H2D and D2H inside the timed region).  Beside the C2 headline the line carries
+  * `configs`: device-resident throughput and roofline fraction of the other BASELINE.json configs (C1, C3 x1..x8,
+    one C4 point per kernel family, C5 shard-sized) - N=1 only, `--no-configs` skips it;
+  * `c5_strong` (N>1): ONE cf32 capture (2^33 samples at N=8), FFT N=65536, frame-range sharded with halo, strong scaling;
+  * `parity_check`: sampled frame groups of the TIMED C2 output against the float64 oracle (pixels off by one colour
+    step, dB error per band), so every bench record carries parity at full size.
 """
 from __future__ import annotations
 
@@ -112,14 +117,20 @@ def window_f64():
 # oracle/, since no JavaScript engine exists in this image), all host threads, fan-out exactly as
 # lib/spectroplot.js:1206-1228 does it (one slice per worker thread).
 # ----------------------------------------------------------------------------------------------
+WORKLOAD = ("C2: cs16 100Mi samples/GPU, FFT N=4096, Blackman-Harris, Viridis, hop N "
+            "(width {width}), dB+colour histograms, min/max/amp gauges")
+
+
 def run_reference(args):
+    """The reference's CPU implementation of the path on the SAME workload as our arm's N=1 run: the whole C2 capture
+    (100 Mi samples, width 25 600) per step, fan-out over all host threads as lib/spectroplot.js:1206-1228."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     from oracle import oracle as O
     cores = os.cpu_count() or 1
-    frames = 512 * cores                                   # bounded sample: 2 Mi samples per core
-    S = frames * N_FFT
+    S = SAMPLES_PER_GPU
+    frames = S // N_FFT
     buf = O.synth(FMT, 0, S, S, SEED)
     w, wt = window_f64()
     cm = viridis_cmap()
@@ -135,11 +146,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2: cs16, FFT N=4096, Blackman-Harris, Viridis, hop N, hist+gauges",
-                       "sample_per_step": f"{S} complex samples ({frames} frames), {cores} worker threads, "
-                                          "fan-out as lib/spectroplot.js:1206-1228"},
+            "config": {"workload": WORKLOAD.format(width=frames), "samples_total": S, "frames_total": frames,
+                       "note": f"the whole C2 capture per step on {cores} worker threads (fan-out as lib/spectroplot.js:1206-1228); "
+                               "at N>1 the reference renders one GPU's share (it has no multi-device path)"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{S} samples per step; C float64 restatement of lib/worker.js (oracle/), "
+                             "sample": f"{S} samples per step (the whole C2 capture); C float64 restatement of lib/worker.js (oracle/), "
                                        "an upper bound on the JS worker's speed"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -187,6 +198,174 @@ def bind_to_gpu_numa_node(index: int):
         return {"node": node, "cpus": len(cpus)}
     except Exception:
         return None
+
+
+
+# ----------------------------------------------------------------------------------------------
+# parity at full size: frame groups of the TIMED output against the float64 oracle (the checker, never the thing measured)
+# ----------------------------------------------------------------------------------------------
+def oracle_parity_sample(eng, torch, d_img, width, total_samples, w, wt, cm, groups=6):
+    """Groups of 8 consecutive frames of the C2 render (first, last, evenly spread): at hop N a group is itself a message
+    of 8N samples with stride N, so the oracle renders exactly the frames the GPU rendered.  Pixels come from the image
+    the timed steps wrote; dB values from the engine's dB tap on the same samples."""
+    from oracle import oracle as O
+    xs = sorted({int(round(i * (width - 8) / max(1, groups - 1))) // 8 * 8 for i in range(groups)})
+    lut = {(int(c[0]) << 16) | (int(c[1]) << 8) | int(c[2]): i for i, c in enumerate(cm)}
+    img = d_img.view(N_FFT, width, 4)
+    off1 = worse = px = 0
+    err_hi = err_lo = 0.0
+    sq_lo, n_lo = 0.0, 0
+    for x in xs:
+        raw = O.synth(FMT, x * N_FFT, 8 * N_FFT, total_samples, SEED)
+        ora = O.render(raw, FMT, N_FFT, 8, w, 1.0 / wt, GAIN, RANGE, cm, taps=True)
+        g = img[:, x:x + 8, :].cpu().numpy().astype(np.int64)
+        key = (g[..., 0] << 16) | (g[..., 1] << 8) | g[..., 2]
+        gi = np.vectorize(lambda k: lut.get(int(k), -1000))(key)                 # colour index per pixel [row][frame]
+        rows = (N_FFT // 2 - np.arange(N_FFT)) % N_FFT                           # bin -> row (lib/worker.js:90)
+        oi = np.empty_like(gi)
+        oi[rows, :] = ora.gray.T.astype(np.int64)                                # oracle taps are [frame][bin]
+        d = np.abs(gi - oi)
+        off1 += int((d == 1).sum()); worse += int((d > 1).sum()); px += d.size
+        db = eng.render_db(raw, FMT, N_FFT, 8, w, 1.0 / wt, GAIN, RANGE, cm)     # [frame][bin], dBfs - gain
+        ref = ora.db
+        # bands on the conventional 20 log10 scale: the reference's dB is 10 log10|X| = half of it
+        e = np.abs(db.astype(np.float64) - ref)
+        hi, lo = ref > -50.0, (ref <= -50.0) & (ref > -60.0)
+        if hi.any(): err_hi = max(err_hi, float(e[hi].max()))
+        if lo.any():
+            err_lo = max(err_lo, float(e[lo].max())); sq_lo += float((e[lo] ** 2).sum()); n_lo += int(lo.sum())
+    return {"frames_checked": 8 * len(xs), "frame_groups_at": xs, "pixels_checked": px, "pixels_off_by_one_step": off1,
+            "pixels_off_by_more": worse, "off_by_one_fraction": off1 / max(1, px),
+            "max_db_err_above_-100dBFS": err_hi, "max_db_err_-120..-100dBFS": err_lo,
+            "rms_db_err_-120..-100dBFS": (sq_lo / n_lo) ** 0.5 if n_lo else 0.0,
+            "checker": "oracle/ (float64 restatement of lib/worker.js pinned to the reference's own replies)"}
+
+
+# ----------------------------------------------------------------------------------------------
+# the other BASELINE.json configs, device resident (N=1): what only builder-run sweeps showed in round 1
+# ----------------------------------------------------------------------------------------------
+def run_config(eng, torch, stream, dev, tag, fmt, n, zoom, window, cmname, S, steps=3):
+    from spectro_b200 import windows, cmaps, _lib
+    sw = _lib.load().sp_sample_width(_lib.format_id(fmt))
+    width = zoom * S // n
+    if zoom > 1:
+        width = width // 8 * 8
+    w = getattr(windows, window + "Window")(n)
+    cm = [list(c) for c in cmaps.cmaps[cmname + "_cmap"]]
+    cm[0] = [0, 0, 0]; cm[-1] = [255, 255, 255]
+    cmb = cmaps.cmap_bytes(cm)
+    nbytes = S * sw
+    d_in = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+    eng.synth_fill(d_in.data_ptr(), fmt, 0, S, S, 0x5EC70010)
+    d_img = torch.empty(4 * width * n, dtype=torch.uint8, device=dev)
+    d_g = torch.empty(3 * width, dtype=torch.uint8, device=dev)
+    d_hist = torch.zeros(1000 + len(cmb), dtype=torch.int64, device=dev)
+    d_mm = torch.zeros(2, dtype=torch.float64, device=dev)
+    ww = np.array(w["window"], np.float64)
+
+    def step():
+        rq, keep = eng.make_request(d_in.data_ptr(), fmt, n, width, ww, 1.0 / float(w["weight"]), 6, 30, cmb, byte_length=nbytes)
+        return eng.render_enqueue(rq, d_img.data_ptr(), (d_g.data_ptr(), d_g.data_ptr() + width, d_g.data_ptr() + 2 * width),
+                                  d_hist.data_ptr(), d_hist.data_ptr() + 8000, d_mm.data_ptr())
+    for _ in range(3):
+        rp = step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        rp = step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    eng.render_finish(rp)
+    total = int(d_hist[1000:].sum().item())
+    alg = S * sw + 4.0 * width * n                                  # SURVEY 8(d): sampleWidth + 4 n / H bytes per sample
+    peak, _ = measured_peaks()
+    out = {"case": tag, "format": fmt, "n": n, "zoom": zoom, "window": window, "cmap": cmname, "samples": S, "width": width,
+           "hop": (S - n) / (width - 1), "ms_per_render": ms, "msamples_s": S / ms / 1e3, "algorithmic_gb": alg / 1e9,
+           "frac_of_measured_hbm": alg / ms / 1e6 / peak, "launches": rp.kernel_launches, "hist_total_ok": total == width * n,
+           "plan": eng.kernel_plan(fmt, n)}
+    del d_in, d_img, d_g
+    torch.cuda.empty_cache()
+    return out
+
+
+def configs_block(eng, torch, stream, dev):
+    """(tag, format, N, zoom, window, colormap, samples).  C3 / C5 are sized to fit one GPU beside each other's buffers:
+    C3 at 2^30 samples (the stated size: images of 4 + 8 + 16 + 32 GiB, one level resident at a time), C5 shard-sized
+    (2^30 of the 2^33 samples: what one of 8 GPUs renders)."""
+    cases = [("C1 cu8 N=1024 Hann Cube1 hop N", "CU8", 1024, 1, "hann", "cube1", 9765 * 1024)]
+    cases += [(f"C3 cf32 N=32768 Inferno zoom x{z}", "CF32", 32768, z, "hann", "inferno", 1 << 30) for z in (1, 2, 4, 8)]
+    cases += [("C4 cs4 N=128 (render_w_kernel)", "CS4", 128, 1, "blackmanHarris", "viridis", 1 << 26),
+              ("C4 cu12 N=512 (render_w_kernel)", "CU12", 512, 1, "blackmanHarris", "viridis", 1 << 26),
+              ("C4 cs16 N=128 (render_w_kernel)", "CS16", 128, 1, "hann", "viridis", 1 << 26),
+              ("C4 cs16 N=256 (render_w_kernel)", "CS16", 256, 1, "hann", "viridis", 1 << 26),
+              ("C4 cs16 N=512 (render_w_kernel)", "CS16", 512, 1, "hann", "viridis", 1 << 26),
+              ("C4 cs4 N=2048 (render_rc_kernel)", "CS4", 2048, 1, "blackmanHarris", "viridis", 1 << 26),
+              ("C4 cu12 N=4096 (render_r64_kernel)", "CU12", 4096, 1, "blackmanHarris", "viridis", 1 << 26),
+              ("C4 cs4 N=16384 (render_big_kernel)", "CS4", 16384, 1, "blackmanHarris", "viridis", 1 << 26),
+              ("C4 cu12 N=65536 (render_big_kernel)", "CU12", 65536, 1, "blackmanHarris", "viridis", 1 << 26),
+              ("C5 cf32 N=65536 Hann hop N, one GPU's shard of the 8 GSample capture", "CF32", 65536, 1, "hann", "viridis", 1 << 30)]
+    out = []
+    for c in cases:
+        try:
+            out.append(run_config(eng, torch, stream, dev, *c))
+        except Exception as ex:                              # a config must never take the headline down with it
+            out.append({"case": c[0], "error": repr(ex)[:300]})
+            torch.cuda.empty_cache()
+    return out
+
+
+def c5_strong(eng, torch, dist, stream, dev, world, rank):
+    """BASELINE.json config 5 as stated, strong scaling over the ranks of this run: ONE cf32 capture (2^30 samples per
+    GPU, i.e. 2^33 at N=8), FFT N = 65536, hop N, contiguous frame ranges with a window-length halo, histograms and
+    min / max merged by one NCCL all-gather.  Returns the record on rank 0."""
+    from spectro_b200 import windows, sharding
+    fmt, n, sw, seed = "CF32", 65536, 8, 0x5EC70005
+    S = (1 << 30) * world
+    W = S // n
+    sh = sharding.plan_shards(S, n, W, world)[rank]
+    width, nbytes = sh["width"], sh["sample_count"] * sw
+    cm = viridis_cmap()
+    wd = windows.hannWindow(n)
+    ww, wt = np.array(wd["window"], np.float64), float(wd["weight"])
+    d_in = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+    eng.synth_fill(d_in.data_ptr(), fmt, sh["sample_first"], sh["sample_count"], S, seed)
+    d_img = torch.empty(4 * width * n, dtype=torch.uint8, device=dev)
+    d_g = torch.empty(3 * width, dtype=torch.uint8, device=dev)
+    d_stats, d_hist, d_mm, d_gath = sharding.stats_buffers(torch, 1000 + len(cm), world, dev)
+    shard = sharding.shard_fields(sh, S, sw, W)
+
+    def step():
+        rq, keep = eng.make_request(d_in.data_ptr(), fmt, n, width, ww, 1.0 / wt, 6, 30, cm, byte_length=nbytes, shard=shard)
+        rp = eng.render_enqueue(rq, d_img.data_ptr(), (d_g.data_ptr(), d_g.data_ptr() + width, d_g.data_ptr() + 2 * width),
+                                d_hist.data_ptr(), d_hist.data_ptr() + 8000, d_mm.data_ptr())
+        sharding.gather_stats(dist, d_stats, d_gath)
+        return rp
+    for _ in range(2):
+        rp = step()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 3
+    e0.record(stream)
+    for _ in range(steps):
+        rp = step()
+    e1.record(stream)
+    dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    eng.render_finish(rp)
+    hist, mn, mx = sharding.fold_gathered(torch, d_gath, 1000 + len(cm))
+    total = int(hist[1000:].sum().item())
+    ms = float(t.item())
+    del d_in, d_img, d_g
+    torch.cuda.empty_cache()
+    alg = S * sw + 4.0 * W * n
+    peak, _ = measured_peaks()
+    return {"case": "C5: ONE cf32 capture, FFT N=65536, hop N, frame-range shards with halo, strong scaling over the ranks",
+            "samples": S, "n": n, "width": W, "gpus": world, "halo_samples": n, "ms_per_render": ms, "msamples_s": S / ms / 1e3,
+            "frac_of_measured_hbm_per_gpu": alg / world / ms / 1e6 / peak, "c_hist_total": total, "hist_total_ok": total == W * n,
+            "dBfs_min": mn, "dBfs_max": mx, "merge": "one NCCL all-gather of {cB_hist, c_hist, min, max} per render"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -342,28 +521,45 @@ def run_ours(args):
     h2d = nbytes_in + 8 * N_FFT // 2 + 4 * len(cm)
     d2h = 4 * width * N_FFT + 3 * width + 8 * (1000 + len(cm)) + 16
 
+    c5 = None
+    if world > 1 and not args.no_configs:
+        img_keep = d_img                                      # (the C2 buffers stay allocated: 1.3 GB of 180)
+        eng.set_stream(stream.cuda_stream)
+        try:
+            c5 = c5_strong(eng, torch, dist, stream, dev, world, rank)
+        except Exception as ex:
+            c5 = {"error": repr(ex)[:300]}
+        eng.set_stream(None)
+
     if rank == 0:
         peak, how = measured_peaks()
         kms = float(np.mean(kern_ms)) if len(kern_ms) else ms_step
         alg_bytes = ALG_BYTES_PER_SAMPLE * sh["sample_count"]
         achieved = alg_bytes / (kms * 1e-3) / 1e9
-        traffic, kname = None, "render kernel of " + eng.kernel_plan(FMT, N_FFT)
+        # DRAM traffic of the dominant kernel comes from an ncu --set full capture (profiles/latest_traffic.json); it is only
+        # quoted when that capture was taken on THIS build of the kernels (sp_build_id), otherwise it is stale and left null
+        traffic, kname, traffic_note = None, "render kernel of " + eng.kernel_plan(FMT, N_FFT), None
         try:
             with open(os.path.join(ROOT, "profiles", "latest_traffic.json")) as f:
                 lt = json.load(f)
+            if lt.get("build_id") == _lib.build_id():
                 traffic, kname = lt.get("dram_bytes_per_launch"), lt.get("kernel", kname)
+                traffic_note = lt.get("source")
+            else:
+                traffic_note = (f"profiles/latest_traffic.json was captured on build {lt.get('build_id')}, this library is "
+                                f"{_lib.build_id()}: stale figure withheld")
         except Exception:
             pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": "C2: cs16 100Mi samples/GPU, FFT N=4096, Blackman-Harris, Viridis, hop N "
-                                       f"(width {total_width}), dB+colour histograms, min/max/amp gauges",
+                "config": {"workload": WORKLOAD.format(width=total_width // world),
                            "samples_total": total_samples, "frames_total": total_width, "sharding": f"frame-range x{world}", "numa_binding": numa,
                            "l2": "inputs (419 MB) and outputs (419 MB) per GPU exceed the 126 MB L2; no flush needed",
                            "kernel_plan": eng.kernel_plan(FMT, N_FFT)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "peak_source": how, "kernel": kname,
+                             "traffic": traffic, "traffic_source": traffic_note, "peak_source": how, "kernel": kname,
+                             "kernel_build": _lib.build_id(),
                              "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms, "steps": e2e_steps},
@@ -372,6 +568,12 @@ def run_ours(args):
                                  "dBfs_max": m_max if world > 1 else rp.dBfs_max}}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_sample()
+            line["parity_check"].update(oracle_parity_sample(eng, torch, d_img, width, total_samples, w, wt, cm))
+        if world == 1 and not args.no_configs:
+            eng.set_stream(stream.cuda_stream)
+            line["configs"] = configs_block(eng, torch, stream, dev)
+        if c5 is not None:
+            line["c5_strong"] = c5
         emit(line)
     if world > 1:
         dist.barrier()
@@ -407,6 +609,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (N=1) / the `c5_strong` record (N>1)")
     ap.add_argument("--kernel-only", action="store_true",
                     help="development: device-resident leg only (no e2e, no cpu leg, no output check) - A/B runs of experiment builds ($SP_LIB)")
     args = ap.parse_args()

@@ -143,8 +143,10 @@ typedef struct sp_reply {
 
 typedef struct sp_engine sp_engine;
 
-/* Library / ABI identification. */
+/* Library / ABI identification.  sp_build_id(): hash of the kernel sources the library was built from
+ * (measurement records name the build they belong to). */
 int sp_abi_version(void);
+const char *sp_build_id(void);
 
 /* Format helpers: lib/samples.js:22,30-155.  Name matching is case-insensitive and
  * follows the reference's alias table; an unknown name maps to SP_CU8 like the

@@ -88,6 +88,10 @@ static const char *const k_names[SP_FORMAT_COUNT] = { "CU4", "CS4", "CU8", "CS8"
                                                        "CU32", "CS32", "CU64", "CS64", "CF32", "CF64" };
 
 extern "C" int sp_abi_version(void) { return SP_ABI_VERSION; }
+#ifndef SP_BUILD_ID
+#define SP_BUILD_ID "unknown"
+#endif
+extern "C" const char *sp_build_id(void) { return SP_BUILD_ID; }
 
 extern "C" int sp_format_from_name(const char *name)
 {

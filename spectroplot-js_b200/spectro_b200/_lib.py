@@ -34,7 +34,7 @@ SYMBOLS = ["sp_abi_version", "sp_format_from_name", "sp_format_name", "sp_sample
            "sp_render_finish", "sp_render_zooms", "sp_decode", "sp_render_db", "sp_device_alloc", "sp_device_free", "sp_memcpy_h2d",
            "sp_memcpy_d2h", "sp_host_alloc_pinned", "sp_host_free_pinned", "sp_device_sync", "sp_synth_fill",
            "sp_synth_lut", "sp_device_count", "sp_sm_count", "sp_kernel_plan", "sp_profile_enable", "sp_profile_read",
-           "sp_render_shards", "sp_select_device"]
+           "sp_render_shards", "sp_select_device", "sp_build_id"]
 
 
 class SpError(RuntimeError):
@@ -74,6 +74,7 @@ def load():
                           "(or make -C spectroplot-js_b200/csrc); there is no CPU fallback")
     lib = C.CDLL(path)
     lib.sp_format_name.restype = C.c_char_p
+    lib.sp_build_id.restype = C.c_char_p
     lib.sp_last_error.restype = C.c_char_p
     lib.sp_last_error.argtypes = [C.c_void_p]
     lib.sp_kernel_plan.restype = C.c_char_p
@@ -107,6 +108,10 @@ def load():
     lib.sp_sm_count.argtypes = [C.c_void_p]
     _lib = lib
     return lib
+
+
+def build_id() -> str:
+    return load().sp_build_id().decode()
 
 
 def format_id(fmt) -> int:
