@@ -525,6 +525,7 @@ def run_ours(args):
     if world > 1 and not args.no_configs:
         img_keep = d_img                                      # (the C2 buffers stay allocated: 1.3 GB of 180)
         eng.set_stream(stream.cuda_stream)
+        eng.profile_enable(0)
         try:
             c5 = c5_strong(eng, torch, dist, stream, dev, world, rank)
         except Exception as ex:
@@ -571,6 +572,7 @@ def run_ours(args):
             line["parity_check"].update(oracle_parity_sample(eng, torch, d_img, width, total_samples, w, wt, cm))
         if world == 1 and not args.no_configs:
             eng.set_stream(stream.cuda_stream)
+            eng.profile_enable(0)                             # no per-launch event pairs: these are whole-render timings
             line["configs"] = configs_block(eng, torch, stream, dev)
         if c5 is not None:
             line["c5_strong"] = c5

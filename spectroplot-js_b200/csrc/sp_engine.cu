@@ -569,6 +569,15 @@ static int prepare(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, boo
     const int n = rq->n;
     j.log2n = ilog2_exact(n);
     j.plan = make_plan(j.log2n);
+    if (j.plan.sub_r == 1 && e->l2_window) {
+        // the last render pinned the pre-pass ring of render_big_kernel in L2: give the cache back to this one
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof av);
+        cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaCtxResetPersistingL2Cache();
+        cudaGetLastError();
+        e->l2_window = 0;
+    }
     j.width = rq->width;
     j.range = rq->range;
     j.gain = rq->gain;
