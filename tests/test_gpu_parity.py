@@ -353,6 +353,62 @@ def test_properties_at_scale(engine):
         assert np.abs(d_).max() <= 1 and (d_ != 0).sum() <= 8
 
 
+@pytest.mark.parametrize("tag,fmt,n,window,S", [
+    ("C1", "CU8", 1024, "hann", 9765 * 1024),                 # BASELINE configs[0]: 10 s @ 1 MS/s, hop N (9 765 frames)
+    ("C2", "CS16", 4096, "blackmanHarris", 100 << 20),        # configs[1], the headline: 100 Mi samples, 25 600 frames
+    ("C3", "CF32", 32768, "hann", 1 << 30),                   # configs[2] at zoom x1: 2^30 samples (8 GiB + a 4 GiB image)
+    ("C4", "CU12", 512, "bartlett", 1 << 26),                 # configs[3]: one packed format on the small-N kernel
+    ("C5", "CF32", 65536, "hann", 1 << 31)])                  # configs[4]: two of the eight shards of the 2^33-sample capture
+def test_baseline_configs_at_full_size(engine, tag, fmt, n, window, S):
+    """BASELINE.json's configurations at their stated sizes, device resident, generated on the device: histogram totals
+    (64-bit counters), and groups of 8 frames - first, last, spread - against the float64 oracle (at hop N a group of 8
+    frames is itself a message of 8 N samples with the same frame positions), pixels and gauges."""
+    from spectro_b200 import _lib
+    sw = _lib.load().sp_sample_width(_lib.format_id(fmt))
+    width = S // n
+    seed = 0x5EC70000 + n
+    w, wt = O.window(window, n)
+    d_in = engine.alloc(S * sw + 256)
+    engine.synth_fill(d_in, fmt, 0, S, S, seed)
+    d_img, d_g = engine.alloc(4 * width * n), engine.alloc(3 * width)
+    d_hist, d_mm = engine.alloc(8 * (1000 + len(CM256))), engine.alloc(16)
+    try:
+        rq, keep = engine.make_request(d_in, fmt, n, width, w, 1 / wt, 6, 30, CM256, byte_length=S * sw)
+        rp = engine.render_enqueue(rq, d_img, (d_g, d_g + width, d_g + 2 * width), d_hist, d_hist + 8000, d_mm)
+        engine.render_finish(rp)
+        hist = np.empty(1000 + len(CM256), np.uint64)
+        engine.d2h(hist, d_hist)
+        assert int(hist[1000:].sum()) == width * n
+        assert width * n - 1000 <= int(hist[:1000].sum()) <= width * n
+        gauges = np.empty(3 * width, np.uint8)
+        engine.d2h(gauges, d_g)
+        rows = (n // 2 - np.arange(n)) % n                                           # bin -> row, lib/worker.js:90
+        groups = sorted({int(round(i * (width - 8) / 4)) // 8 * 8 for i in range(5)})
+        off1 = px = 0
+        for x in groups:
+            raw = O.synth(fmt, x * n, 8 * n, S, seed)
+            ora = O.render(raw, fmt, n, 8, w, 1 / wt, 6, 30, CM256, taps=True)
+            # the group's pixels: 8 consecutive columns of every image row (32 bytes at pitch 4 * width)
+            tile = np.empty((n, 8, 4), np.uint8)
+            row = np.empty(32, np.uint8)
+            for y in range(0, n, max(1, n // 512)):                                   # up to 512 rows per group keep the test quick
+                engine.d2h(row, d_img + 4 * (y * width + x))
+                tile[y] = row.reshape(8, 4)
+            ys = np.arange(0, n, max(1, n // 512))
+            gi = cmap_index_image(tile[ys], CM256)
+            oi = np.empty((n, 8), np.int64)
+            oi[rows, :] = ora.gray.T.astype(np.int64)
+            d = np.abs(gi - oi[ys])
+            assert d.max() <= 1, (tag, x, int(d.max()))
+            off1 += int((d == 1).sum()); px += d.size
+            for k, name in enumerate(("gauge_mins", "gauge_maxs", "gauge_amps")):
+                assert np.abs(gauges[k * width + x:k * width + x + 8].astype(int) - getattr(ora, name).astype(int)).max() <= 1, (tag, name, x)
+        assert off1 <= max(2, int(1e-3 * px)), (tag, off1, px)
+    finally:
+        for d in (d_in, d_img, d_g, d_hist, d_mm):
+            engine.free(d)
+
+
 # ------------------------------------------------------------------ pipelined host path == single shot
 @pytest.mark.parametrize("case", [("CS16", 1024, 1000, 700, False), ("CU8", 256, 4001, 300, False),
                                   ("CS16", 4096, 800, 4096, False), ("CF32", 512, 1500, 512, True),
