@@ -323,6 +323,21 @@ template <int FMT> __device__ __forceinline__ cf decode_raw_cf(const uint8_t *__
         const unsigned v = *reinterpret_cast<const unsigned *>(buf + 4 * s) ^ 0x80008000u;
         const cf u = cpk(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7610)), __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7632)));
         return cadd(u, cpk(-8421376.0f, -8421376.0f));
+    } else if constexpr (FMT == CU8 || FMT == CS8) {
+        // 8-bit codes without the conversion unit (two I2F per sample are 1/8 cycle of the 16-lane XU pipe, which the
+        // log2 of the epilogue also needs): each byte is dropped into the mantissa of 2^23 (one PRMT; CS8 is biased to
+        // unsigned first), the bias leaves with one FADD2, and the CU8 scaling (2c - 255) / 255 is the same correctly
+        // rounded Markstein division as cv_u8(), issued on both components at once.  Every step is exact or identical
+        // to decode_fast<>(): the results are bit-identical (tests: test_decode_bit_exact + the fused-kernel parity).
+        unsigned v = *reinterpret_cast<const unsigned short *>(buf + 2 * s);
+        if constexpr (FMT == CS8) v ^= 0x8080u;
+        const cf u = cpk(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7650)), __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7651)));
+        if constexpr (FMT == CS8) return cadd(u, cpk(-8388736.0f, -8388736.0f));            // c = u - 2^23 - 128 (scale 1/128 folded into the window)
+        const cf c = cadd(u, cpk(-8388608.0f, -8388608.0f));                                // c = 0 .. 255
+        const cf x = cfma2(c, cpk(2.0f, 2.0f), cpk(-255.0f, -255.0f));                      // 2c - 255, exact
+        constexpr float r = 1.0f / 255.0f;
+        const cf q = cmul2(x, cpk(r, r));
+        return cfma2(cfma2(q, cpk(-255.0f, -255.0f), x), cpk(r, r), q);                     // div_exact<255>, both halves
     } else {
         return cpk(decode_raw<FMT>(buf, s, rt_fmt));
     }

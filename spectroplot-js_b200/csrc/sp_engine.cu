@@ -471,22 +471,28 @@ extern "C" const char *sp_kernel_plan(sp_engine *e, int format, int n, int chann
     e = dev0(e);
     if (!e) return "";
     const int l = ilog2_exact(n);
-    char buf[384];
+    char buf[640];
     if (l < 1 || l > 18 || format < 0 || format >= SP_FORMAT_COUNT) { e->plan = "unsupported"; return e->plan.c_str(); }
     Plan pl = make_plan(l);
-    snprintf(buf, sizeof buf, "%s%srender_kernel<N=%d,%s> tile=%d frames smem_x=%d B%s", pl.sub_r > 1 ? "prepass_kernel<R=" : "",
-             pl.sub_r > 1 ? (std::to_string(pl.sub_r) + "> + ").c_str() : "", 1 << pl.log2k,
-             specialised(format) ? k_names[format] : "runtime-format", pl.tile, pl.smem_x * 8, channel_mode ? " +splitreal" : "");
-    if (pl.log2k >= 8 && pl.log2k <= 11 && !channel_mode && !getenv("SP_NO_FAST") && rc_for(format) && sp::sample_width(format) <= 8) {
-        const size_t l = strlen(buf);
-        snprintf(buf + l, sizeof buf - l, " | fast path (spectrogram and waterfall): render_rc_kernel<N=64x%d, tile=%d frames> (one exchange, joint histogram, TMA-staged input)",
-                 (1 << pl.log2k) / 64, 65536 >> pl.log2k);
-    }
-    if (pl.log2k == 12 && !channel_mode && !getenv("SP_NO_FAST")) {
-        const size_t l = strlen(buf);
-        if ((pl.sub_r > 1 ? sp_r64_cf32 != nullptr : r64_for(format) != nullptr) && (pl.sub_r > 1 || sp::sample_width(format) <= 8))
-            snprintf(buf + l, sizeof buf - l, " | fast path (spectrogram and waterfall): render_r64_kernel<streams=4,tile=16 frames> (64x64 FFT, one exchange, joint histogram, TMA-staged input)");
-    }
+    const char *fname = specialised(format) ? k_names[format] : "runtime-format";
+    const bool fast_ok = !getenv("SP_NO_FAST") && sp::sample_width(format) <= 8 && specialised(format);
+    size_t o = 0;
+    // the kernel the bulk of a spectrogram-layout message takes, then what catches the rest
+    if (pl.sub_r > 1 && !channel_mode && !getenv("SP_NO_FAST") && big_for(format))
+        o += snprintf(buf + o, sizeof buf - o, "render_big_kernel<%s> (n = %d x 4096 in one persistent launch: pre-pass and 64x64 second stage as queue items over an "
+                      "L2-resident ring, joint histogram, store warpgroup) | ", fname, pl.sub_r);
+    else if (pl.log2k == 12 && pl.sub_r == 1 && fast_ok && r64_for(format))
+        o += snprintf(buf + o, sizeof buf - o, "render_r64_kernel<%s> (64x64 FFT, one exchange, 4 frame streams + store warpgroup, TMA-staged input, joint histogram, "
+                      "RGBA tiles + tensor-TMA row stores%s) | ", fname, channel_mode ? ", split-real in the FFT warps" : "");
+    else if (pl.log2k >= 6 && pl.log2k <= 10 && !channel_mode && fast_ok && w_for(format))
+        o += snprintf(buf + o, sizeof buf - o, "render_w_kernel<%s, N=%dx%d> (warp-synchronous, one exchange, span-staged input, tables in registers, joint histogram, "
+                      "store warpgroup; waterfall: render_rc_kernel / render_kernel) | ", fname, pl.log2k <= 6 ? 8 : (pl.log2k <= 8 ? 16 : 32),
+                      (1 << pl.log2k) / (pl.log2k <= 6 ? 8 : (pl.log2k <= 8 ? 16 : 32)));
+    else if (pl.log2k >= 8 && pl.log2k <= 11 && !channel_mode && fast_ok && rc_for(format))
+        o += snprintf(buf + o, sizeof buf - o, "render_rc_kernel<%s, N=64x%d> (one exchange, joint histogram, TMA-staged input, store warpgroup) | ", fname, (1 << pl.log2k) / 64);
+    snprintf(buf + o, sizeof buf - o, "%s%srender_kernel<N=%d,%s> tile=%d frames%s (every option; remainder frames, ragged ends, dB tap, cmap_len > 256)",
+             pl.sub_r > 1 ? "prepass_kernel<R=" : "", pl.sub_r > 1 ? (std::to_string(pl.sub_r) + "> + ").c_str() : "", 1 << pl.log2k, fname, pl.tile,
+             channel_mode ? " +splitreal" : "");
     e->plan = buf;
     return e->plan.c_str();
 }
