@@ -581,6 +581,7 @@ static int prepare(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, boo
         memset(&av, 0, sizeof av);
         cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &av);
         cudaCtxResetPersistingL2Cache();
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);    // the set-aside half of the L2 is not available to normal lines while it stands
         cudaGetLastError();
         e->l2_window = 0;
     }
@@ -814,15 +815,16 @@ static int launch_big_kernel(sp_engine *e, big_fn fn, Params &q, long long *nfas
     if (occ < 1) { *nfast = 0; return SP_OK; }
     const int env_slots = getenv("SP_BIG_SLOTS") ? atoi(getenv("SP_BIG_SLOTS")) : 0;       // tuning / tests: ring slots and pre-pass lead
     const int env_lead = getenv("SP_BIG_LEAD") ? atoi(getenv("SP_BIG_LEAD")) : 0;
-    // Ring: 80 MB of the 126 MB L2 (every CTA holds 512 KB of it for the length of a second-stage tile, so a smaller ring
-    // makes the pre-pass wait for free slots and a larger one spills to HBM - profiles/r02_big_kernel.txt), at least 8 blocks;
-    // the pre-pass runs L = 0.4 S blocks ahead of the second stage.
+    // Ring: 64 MB, half of the L2 (every CTA holds 512 KB of it for the length of a second-stage tile: with less the pre-pass
+    // waits for free slots, with more the ring no longer fits the 79 MB that can be pinned and spills to HBM - ncu: 1.0 x the
+    // algorithmic DRAM traffic at 64 MB, 1.23 x at 80 MB; profiles/r02_big_kernel.txt), at least 8 blocks; the pre-pass runs
+    // L = 3 S / 8 blocks ahead of the second stage.
     const size_t block_bytes = (size_t)8 * (size_t)n * 8;
-    int S = env_slots > 0 ? env_slots : (int)(((size_t)80 << 20) / block_bytes);
+    int S = env_slots > 0 ? env_slots : (int)(((size_t)64 << 20) / block_bytes);
     if (S < 8 && env_slots <= 0) S = 8;
     if (S < 2) S = 2;
     if (S > 64) S = 64;
-    int L = env_lead > 0 ? env_lead : (2 * S / 5 > 2 ? 2 * S / 5 : 2);
+    int L = env_lead > 0 ? env_lead : (3 * S / 8 > 2 ? 3 * S / 8 : 2);
     if (L > S) L = S;
     if (L < 1) L = 1;
     const float2 *tw14 = nullptr, *twT = nullptr;

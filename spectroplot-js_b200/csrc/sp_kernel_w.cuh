@@ -35,7 +35,11 @@ template <int LOG2P, int LOG2T, int FMT> struct WCfg {
     static constexpr bool OK = (FMT != FMT_RUNTIME) && SWB <= 8 && T <= P && T >= 8;
     static constexpr int XP = T + 2;                                             // exchange row pitch (float2): LDS.128 of 8 lanes conflict-free
     static constexpr int FSTR = P * XP + ((T == 8 && (P * XP) % 16 != 8) ? 8 : 0);   // float2 per frame: STS.64 of two frames in a half-warp conflict-free
-    static constexpr int RAWP = N * SWB + 32;                                    // bytes per raw frame slot
+    // bytes per raw frame slot: the frame, 16 bytes of alignment slack at either end, and a pad that puts the FW frames a warp
+    // decodes with ONE load instruction (T lanes x SWB bytes each) into different banks
+    // (a multiple of 16 bytes: bulk-copy destination)
+    static constexpr int RAWP = N * SWB + ((T * SWB >= 128 || T * SWB < 16 || (T * SWB) % 16 != 0) ? 32 : (T * SWB >= 32 ? T * SWB : T * SWB + 128));
+    static_assert(RAWP % 16 == 0, "raw slots are bulk-copy destinations");
     static constexpr int XBYTES = ((FW * FSTR * 8 > FW * RAWP ? FW * FSTR * 8 : FW * RAWP) + 15) & ~15;
     static constexpr int FPITCH = (HF + 31) / 32 * 32 + FW;                      // staging words per word column: STS.32 of a warp conflict-free
     static constexpr int HALF_WORDS = (N / 4) * FPITCH;
@@ -92,9 +96,9 @@ __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_
         }
         int *off = s_off + (warp * 2 + par) * FW;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        // overlapping (or touching) frames: ONE copy of the span, every frame decodes from its own offset in it
+        // overlapping frames (hop < N): ONE copy of the span, every frame decodes from its own offset in it
         const long long span = p0[FW - 1] - p0[0] + N;
-        if (FW > 1 && span * B::SWB + 32 <= FW * B::RAWP && !(p.dbg & 16)) {     // (SP_DEBUG_SKIP=16: per-frame copies, for the A/B of the reuse counters)
+        if (FW > 1 && span < (long long)FW * N && span * B::SWB + 32 <= FW * B::RAWP && !(p.dbg & 16)) {     // (SP_DEBUG_SKIP=16: per-frame copies, for the A/B of the reuse counters)
             const unsigned long long o0 = (unsigned long long)p0[0] * B::SWB, a0 = o0 & ~15ull;
             const unsigned bytes = (unsigned)(((o0 - a0) + (unsigned long long)span * B::SWB + 15) & ~15ull);
 #pragma unroll

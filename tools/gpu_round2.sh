@@ -17,7 +17,7 @@ timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k re
     python tools/sweep.py C5 1 > $OUT/ncu_full_big_$TAG.log 2>&1
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sectors_op_read.sum,lts__t_sector_op_read_hit_rate.pct,l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum,smsp__inst_executed.sum
 for dbg in 0 16; do
-  SP_DEBUG_SKIP=$dbg timeout -s KILL 400 ncu --metrics $M --clock-control none -k regex:render_w_ -s 3 -c 1 --csv --log-file $OUT/overlap_w_dbg${dbg}_$TAG.csv \
+  SP_DEBUG_SKIP=$dbg timeout -s KILL 400 ncu --metrics $M --clock-control none -k regex:render_w_ -c 40 --csv --log-file $OUT/overlap_w_dbg${dbg}_$TAG.csv \
       python tools/sweep.py X:CS16:128:1:24,X:CS16:128:2:24,X:CS16:128:4:24,X:CS16:128:8:24,X:CS16:256:4:24,X:CS16:512:4:24 1 > $OUT/overlap_w_dbg${dbg}_$TAG.log 2>&1
 done
 CASES=$(for n in 64 128 256 512 1024 2048 4096 8192 16384 32768 65536 131072; do echo -n "X:CS16:$n:1:26,"; done)
