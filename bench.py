@@ -306,13 +306,23 @@ def configs_block(eng, torch, stream, dev):
               ("C4 cs4 N=16384 (render_big_kernel)", "CS4", 16384, 1, "blackmanHarris", "viridis", 1 << 26),
               ("C4 cu12 N=65536 (render_big_kernel)", "CU12", 65536, 1, "blackmanHarris", "viridis", 1 << 26),
               ("C5 cf32 N=65536 Hann hop N, one GPU's shard of the 8 GSample capture", "CF32", 65536, 1, "hann", "viridis", 1 << 30)]
+    # the four-step sizes exist in two forms (csrc/sp_engine.cu): the L2-ring kernel (1.0 x DRAM traffic; chosen by default for
+    # these two long captures) and the round-1 HBM-scratch pair - both are reported
+    cases += [("C3 cf32 N=32768 zoom x1, HBM-scratch form (SP_FOURSTEP=hbm)", "CF32", 32768, 1, "hann", "inferno", 1 << 30),
+              ("C5 cf32 N=65536, HBM-scratch form (SP_FOURSTEP=hbm)", "CF32", 65536, 1, "hann", "viridis", 1 << 30)]
     out = []
     for c in cases:
+        hbm = "SP_FOURSTEP=hbm" in c[0]
+        if hbm:
+            os.environ["SP_FOURSTEP"] = "hbm"
         try:
             out.append(run_config(eng, torch, stream, dev, *c))
         except Exception as ex:                              # a config must never take the headline down with it
             out.append({"case": c[0], "error": repr(ex)[:300]})
             torch.cuda.empty_cache()
+        finally:
+            if hbm:
+                os.environ.pop("SP_FOURSTEP", None)
     return out
 
 

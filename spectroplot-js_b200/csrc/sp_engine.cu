@@ -479,8 +479,9 @@ extern "C" const char *sp_kernel_plan(sp_engine *e, int format, int n, int chann
     size_t o = 0;
     // the kernel the bulk of a spectrogram-layout message takes, then what catches the rest
     if (pl.sub_r > 1 && !channel_mode && !getenv("SP_NO_FAST") && big_for(format))
-        o += snprintf(buf + o, sizeof buf - o, "render_big_kernel<%s> (n = %d x 4096 in one persistent launch: pre-pass and 64x64 second stage as queue items over an "
-                      "L2-resident ring, joint histogram, store warpgroup) | ", fname, pl.sub_r);
+        o += snprintf(buf + o, sizeof buf - o, "four-step n = %d x 4096: render_big_kernel<%s> (one persistent launch, pre-pass and 64x64 second stage as queue items over an "
+                      "L2-resident ring; long captures at n = 32768 / 65536, SP_FOURSTEP=ring) or prepass_kernel + render_r64_kernel<sub-frame> over an HBM scratch | ",
+                      pl.sub_r, fname);
     else if (pl.log2k == 12 && pl.sub_r == 1 && fast_ok && r64_for(format))
         o += snprintf(buf + o, sizeof buf - o, "render_r64_kernel<%s> (64x64 FFT, one exchange, 4 frame streams + store warpgroup, TMA-staged input, joint histogram, "
                       "RGBA tiles + tensor-TMA row stores%s) | ", fname, channel_mode ? ", split-real in the FFT warps" : "");
@@ -1040,9 +1041,16 @@ static int enqueue_frames(sp_engine *e, Job &j, Params &p)
         sp::init_minmax_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, e->stream>>>((unsigned *)p.fmin, (unsigned *)p.fmax, nf);
         e->launches++;
         long long big_done = 0;
-        // SP_FOURSTEP=hbm selects the round-1 form (pre-pass kernel -> 1 GB scratch in HBM -> second-stage kernel) for A/B runs
-        static const bool hbm_scratch = getenv("SP_NO_BIG") || (getenv("SP_FOURSTEP") && !strcmp(getenv("SP_FOURSTEP"), "hbm"));
-        if (!tap && fused_eligible(p) && big_for(fmt) && !hbm_scratch) {
+        // Two forms of the four-step transform (measured side by side: profiles/r02_fourstep_paths.txt):
+        //   ring  render_big_kernel: ONE persistent launch, the pre-pass output stays in an L2-resident ring - DRAM traffic 1.0 x the
+        //         algorithmic bytes, but its pre-pass runs at one CTA per SM and is bound by the SM's load / store issue rate;
+        //   hbm   prepass_kernel -> 1 GB scratch in HBM -> second-stage kernel: 2.3 x the traffic, a well-occupied pre-pass.
+        // The ring form is as fast or faster where the scratch round trip hurts most - n = 32768 / 65536 on long captures (C3, C5) -
+        // and slower elsewhere, so it is chosen there; SP_FOURSTEP=ring / hbm forces one form (tests, A/B runs).
+        const char *force = getenv("SP_FOURSTEP");
+        const bool force_hbm = getenv("SP_NO_BIG") || (force && !strcmp(force, "hbm")), force_ring = force && !strcmp(force, "ring");
+        const bool ring = force_ring || (!force_hbm && (R == 8 || R == 16) && (double)nf * (double)n >= 536870912.0);
+        if (!tap && fused_eligible(p) && big_for(fmt) && ring) {
             Params q = p;
             if ((rc = launch_big_kernel(e, big_for(fmt), q, &big_done))) return rc;
         }

@@ -263,6 +263,7 @@ def test_degenerate_messages_are_answered_like_the_reference(engine, fmt, n, wid
 def test_big_kernel_ring_wraps(engine, monkeypatch, n, width, slots, lead):
     """render_big_kernel with a ring of only 4-5 blocks: every slot is reused several times (P waits for the F items of the
     slot's previous block, F for the 32 P items of its own), overlapping hops, the < 8-frame remainder on the generic path."""
+    monkeypatch.setenv("SP_FOURSTEP", "ring")              # (short captures take the HBM-scratch form by default)
     if slots:
         monkeypatch.setenv("SP_BIG_SLOTS", str(slots))
         monkeypatch.setenv("SP_BIG_LEAD", str(lead))
@@ -273,9 +274,12 @@ def test_big_kernel_ring_wraps(engine, monkeypatch, n, width, slots, lead):
     assert np.array_equal(g2["image"], gpu["image"]) and np.array_equal(g2["cB_hist"], gpu["cB_hist"])     # repeatable
 
 
+@pytest.mark.parametrize("form", ["ring", "hbm"])
 @pytest.mark.parametrize("n,width", [(131072, 8), (262144, 4)])
-def test_sizes_above_65536(engine, n, width):
-    """lib/fft_nayuki.js:38-39 accepts any power of two; the four-step path covers n up to 262144 (pre-pass radix 32 / 64)."""
+def test_sizes_above_65536(engine, monkeypatch, n, width, form):
+    """lib/fft_nayuki.js:38-39 accepts any power of two; the four-step path covers n up to 262144 (pre-pass radix 32 / 64),
+    in both of its forms."""
+    monkeypatch.setenv("SP_FOURSTEP", form)
     S = n * 2 + 77
     raw = O.synth("CS16", 0, S, S, 5).tobytes()
     run_both(engine, raw, "CS16", n, width, "blackmanHarris", want_db=True)
@@ -514,8 +518,10 @@ def test_r64_non_finite_pixels(engine):
     assert np.array_equal(g2[keep], g[keep])
 
 
+@pytest.mark.parametrize("form", ["ring", "hbm"])
 @pytest.mark.parametrize("n,width", [(8192, 32), (16384, 48), (32768, 16), (65536, 16)])
-def test_r64_four_step(engine, n, width):
+def test_r64_four_step(engine, monkeypatch, n, width, form):
+    monkeypatch.setenv("SP_FOURSTEP", form)
     S = n * width // 2 + n + 9                                 # ~50 % overlap
     buf = O.synth("CS16", 0, S, S, 0x5EC7A100 + n).tobytes()
     run_both(engine, buf, "CS16", n, width, "hann", want_db=False)
