@@ -20,7 +20,16 @@ cases = [("CS16", 4096, 32, False, False),      # render_r64_kernel, full tiles
          ("CS16", 16384, 9, False, True),       # four-step + spectrum epilogue
          ("CS16", 4096, 40, True, False),       # waterfall rows from the r64 store warps (full + partial tile)
          ("CU8", 1024, 72, True, False),        # waterfall rows from the rc store warps
-         ("CF32", 256, 300, True, False)]       # rc C = 4, waterfall
+         ("CF32", 256, 300, True, False),       # rc C = 4, waterfall
+         # round 2
+         ("CS16", 4096, 64, False, False),      # r64 with tensor-TMA row stores (width % 8 == 0: RGBA tiles, UTMASTG)
+         ("CS16", 128, 296, False, False),      # render_w_kernel 16 x 8, 4 frames per warp, span staging (overlapping hops), partial tile
+         ("CU8", 512, 104, False, False),       # render_w_kernel 32 x 16 (twiddles from shared memory)
+         ("CF32", 1024, 56, False, False),      # render_w_kernel 32 x 32
+         ("CU12", 64, 520, False, False),       # render_w_kernel 8 x 8
+         ("CF32", 8192, 40, False, False),      # four-step, L2-ring form (render_big_kernel; SP_FOURSTEP=ring below)
+         ("CS16", 65536, 24, False, False)]     # ring form, R = 16
+os.environ.setdefault("SP_FOURSTEP", "ring")   # cases 7, 8 predate the ring kernel and ask for it too now; the HBM form keeps its round-1 record
 only = [int(a) for a in sys.argv[1:]]
 for i, (fmt, n, width, wf, chm) in enumerate(cases):
     if only and i not in only:
