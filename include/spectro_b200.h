@@ -239,6 +239,9 @@ void sp_synth_lut(int16_t *lut4096);
  * record one around every render-kernel launch (ring).  sp_profile_read() synchronises and
  * returns up to `max` most recent durations in milliseconds (oldest first) and clears the ring. */
 int sp_profile_enable(sp_engine *e, int slots);
+/* Bracket only every `every`-th render-kernel launch (an event pair between dependent kernels costs the stream a few
+ * microseconds: the ring then samples the launches instead of slowing every step).  Reset to 1 by sp_profile_enable. */
+int sp_profile_sample(sp_engine *e, int every);
 int sp_profile_read(sp_engine *e, float *ms, int max);
 
 /* Introspection used by the bench / tests. */

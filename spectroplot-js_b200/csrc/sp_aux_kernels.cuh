@@ -20,50 +20,49 @@ __device__ __forceinline__ unsigned char u8clamped(double v)
     return (unsigned char)__double2int_rn(v);
 }
 
-// gauges (lib/worker.js:128-136) and the message-wide min / max (lib/worker.js:124-125).
-// Many CTAs of 256 frames each; the last CTA to finish converts the folded min/max to doubles.
-// `ordered` says fmin/fmax hold f2ord() encodings (sub-frame mode).  mm = {ordered min, ordered max,
-// done counter}, initialised by prep_kernel.
-// One launch that resets everything a render accumulates into: both histograms, the joint histogram and the
-// min / max fold of finalize_kernel.
-__global__ void __launch_bounds__(256) prep_kernel(unsigned long long *cb, unsigned long long *c, int cmap_len, unsigned *mm,
-                                                   unsigned long long *jh)
+// Decode table of the joint histogram: entry j = (dB bin or -1, colour index), or (-2, 0) when no level maps to j.  It depends only
+// on the dB / colour constants of the message, so it is rebuilt (one tiny launch) only when they change; finalize_kernel then
+// scatters the joint counters with two atomics per non-empty entry instead of a 32-step bisection each.
+__global__ void __launch_bounds__(256) jh_table_kernel(JhConst jc, int cmax, int2 *table)
 {
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i < CB_BINS) cb[i] = 0;
-    if (i < JH_SIZE) jh[i] = 0;
-    if (i < cmap_len) c[i] = 0;
-    if (i == 0) {
-        mm[0] = f2ord(0.0f);        // lib/worker.js:35
-        mm[1] = f2ord(-200.0f);     // lib/worker.js:36
-        mm[2] = 0;
-    }
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= JH_BINS) return;
+    int bin, g;
+    const bool hit = jh_decode(j, jc, cmax, bin, g);
+    table[j] = hit ? make_int2(bin, g < 0 ? 0 : g) : make_int2(-2, 0);
 }
 
+// gauges (lib/worker.js:128-136), the message-wide min / max (lib/worker.js:124-125) and the two histograms of the reply.
+// Every kernel of a render accumulates into engine-owned counters - acc_cb / acc_c (64-bit dB / colour histograms, generic kernel)
+// and jh (joint histogram, fused kernels) - which are all zero when a render starts.  Many CTAs of 256 frames each fold the per-frame
+// values and scatter jh into acc; the LAST CTA to finish publishes min / max as doubles, copies acc to the reply's histograms and
+// zeroes every counter again, so no launch is needed to reset anything before the next render.
+// `ordered` says fmin/fmax hold f2ord() encodings (sub-frame mode).  mm = {ordered min, ordered max, done counter}.
 __global__ void __launch_bounds__(256) finalize_kernel(const float *fmin, const float *fmax, const float2 *fmid,
                                                        long long nframes, double range, double gain, int ordered,
                                                        unsigned char *gmin, unsigned char *gmax, unsigned char *gamp,
                                                        unsigned *mm, double *stats /* [2] min, max */,
-                                                       const unsigned long long *jh, JhConst jc, int cmap_len,
+                                                       unsigned long long *jh, const int2 *jh_table, int cmap_len,
+                                                       unsigned long long *acc_cb, unsigned long long *acc_c,
                                                        unsigned long long *cb_hist, unsigned long long *c_hist)
 {
     __shared__ float s_mn[8], s_mx[8];
-    // joint histogram of render_r64_kernel -> the reference's two histograms (lib/worker.js:106,113)
+    __shared__ int s_last;
+    // joint histogram of the fused kernels -> the reference's two histograms (lib/worker.js:106,113)
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < JH_SIZE; j += gridDim.x * blockDim.x) {
         const unsigned long long c = jh[j];
         if (!c) continue;
         if (j == JH_ZERO) {                          // d0 = -inf pixels were counted in bin 999: they belong to bin 0
-            atomicAdd(&cb_hist[0], c);
-            atomicAdd(&cb_hist[CB_BINS - 1], 0ull - c);
+            atomicAdd(&acc_cb[0], c);
+            atomicAdd(&acc_cb[CB_BINS - 1], 0ull - c);
         } else if (j == JH_BAD) {                    // d0 = +inf / NaN pixels were dropped: they belong to bin 0
-            atomicAdd(&cb_hist[0], c);
+            atomicAdd(&acc_cb[0], c);
         } else if (j == JH_NAN) {                    // ~~(0.5 + NaN) == 0 (lib/worker.js:112)
-            atomicAdd(&c_hist[0], c);
+            atomicAdd(&acc_c[0], c);
         } else if (j < JH_BINS) {
-            int bin, g;
-            jh_decode(j, jc, cmap_len - 1, bin, g);
-            if (bin >= 0) atomicAdd(&cb_hist[bin], c);
-            atomicAdd(&c_hist[g < 0 ? 0 : g], c);
+            const int2 t = jh_table[j];
+            if (t.x >= 0) atomicAdd(&acc_cb[t.x], c);
+            if (t.x > -2) atomicAdd(&acc_c[t.y], c);
         }
     }
     float mn = 0.0f, mx = -200.0f;
@@ -86,18 +85,29 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float *fmin, const 
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
     }
     if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x / 32] = mn; s_mx[threadIdx.x / 32] = mx; }
-    __syncthreads();
+    __syncthreads();                                           // (also: this CTA's scatter atomics have been issued)
     if (threadIdx.x == 0) {
         for (int w = 1; w < (int)(blockDim.x / 32); w++) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); }
         atomicMin(&mm[0], f2ord(mn));
         atomicMax(&mm[1], f2ord(mx));
         __threadfence();
-        if (atomicAdd(&mm[2], 1u) == gridDim.x - 1) {          // last CTA: publish
-            __threadfence();
-            stats[0] = (double)ord2f(atomicMin(&mm[0], 0xffffffffu));
-            stats[1] = (double)ord2f(atomicMax(&mm[1], 0u));
-        }
+        s_last = atomicAdd(&mm[2], 1u) == gridDim.x - 1;
     }
+    __syncthreads();
+    if (!s_last) return;
+    // last CTA: everything every other CTA added is visible (its fence came before its ticket)
+    __threadfence();
+    if (threadIdx.x == 0) {
+        stats[0] = (double)ord2f(*reinterpret_cast<volatile unsigned *>(&mm[0]));
+        stats[1] = (double)ord2f(*reinterpret_cast<volatile unsigned *>(&mm[1]));
+        mm[0] = f2ord(0.0f);        // lib/worker.js:35
+        mm[1] = f2ord(-200.0f);     // lib/worker.js:36
+        mm[2] = 0;
+    }
+    volatile unsigned long long *vcb = acc_cb, *vc = acc_c;
+    for (int i = threadIdx.x; i < CB_BINS; i += blockDim.x) { cb_hist[i] = vcb[i]; vcb[i] = 0; }
+    for (int i = threadIdx.x; i < cmap_len; i += blockDim.x) { c_hist[i] = vc[i]; vc[i] = 0; }
+    for (int i = threadIdx.x; i < JH_SIZE; i += blockDim.x) jh[i] = 0;
 }
 
 // decode tap (sp_decode): same device functions as the fused kernel

@@ -172,12 +172,17 @@ struct sp_engine {
     DevBuf pin[2], pimg[2];                  // pipeline: double-buffered input bytes / image tiles
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_comp[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr }, ev_setup = nullptr;
+    DevBuf acc, jhtab;                       // self-cleaning 64-bit histogram accumulators [1000 + SP_MAX_CMAP]; decode table of the joint histogram
+    float jhtab_key[5] = { 0, 0, 0, 0, -1 };  // constants the table was built for (jA, jB, jC, jD, cmap_len)
+    bool acc_dirty = true;                   // a render was abandoned half way (or nothing is initialised yet): reset the accumulators first
     DevBuf ring, ringctl;                    // n > 4096: L2-resident pre-pass ring and its queue / hand-off counters
     size_t l2_window = 0;                    // bytes of the ring currently covered by the persisting access-policy window
     DevBuf in, zin, spec, image, fmin, fmax, fmid, gauges, hist, jhist, stats, mm, lut, window, window_t, scratch, db, synth_lut;
     // state of an enqueued (not yet finished) render
     std::vector<cudaEvent_t> prof0, prof1;   // per-launch timing ring of the render kernel
-    long long prof_count = 0;
+    long long prof_count = 0, prof_seq = 0;
+    int prof_every = 1;
+    bool prof_this = false;
     std::vector<float> h_window, h_window_t; // last uploaded window / LUT (upload only on change)
     std::vector<uint32_t> h_lut;
     double *stats_src = nullptr;
@@ -311,7 +316,7 @@ extern "C" void sp_destroy(sp_engine *e)
     for (auto &kv : e->twA) cudaFree(kv.second);
     for (auto &kv : e->twB) cudaFree(kv.second);
     DevBuf *bufs[] = { &e->in, &e->zin, &e->spec, &e->image, &e->fmin, &e->fmax, &e->fmid, &e->gauges, &e->hist, &e->jhist, &e->stats, &e->mm,
-                       &e->lut, &e->window, &e->window_t, &e->ring, &e->ringctl, &e->scratch, &e->db, &e->synth_lut, &e->pin[0], &e->pin[1],
+                       &e->lut, &e->window, &e->window_t, &e->acc, &e->jhtab, &e->ring, &e->ringctl, &e->scratch, &e->db, &e->synth_lut, &e->pin[0], &e->pin[1],
                        &e->pimg[0], &e->pimg[1] };
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (auto ev : e->prof0) cudaEventDestroy(ev);
@@ -512,14 +517,17 @@ struct Job {
     bool pipelined = false;    // host buffers streamed chunk by chunk: no whole-message device copies
 };
 
-// bracket a render-kernel launch with the next event pair of the profiling ring
+// bracket a render-kernel launch with the next event pair of the profiling ring.  An event pair between two dependent kernels
+// costs the stream several microseconds (the next launch can no longer be queued behind the running kernel), so only every
+// prof_every-th launch is bracketed (sp_profile_enable's `every`, default 1): the ring then holds a sample of the launches.
 static void prof_begin(sp_engine *e)
 {
-    if (!e->prof0.empty()) cudaEventRecord(e->prof0[e->prof_count % (long long)e->prof0.size()], e->stream);
+    e->prof_this = !e->prof0.empty() && (e->prof_seq++ % (long long)e->prof_every) == 0;
+    if (e->prof_this) cudaEventRecord(e->prof0[e->prof_count % (long long)e->prof0.size()], e->stream);
 }
 static void prof_end(sp_engine *e)
 {
-    if (!e->prof0.empty()) { cudaEventRecord(e->prof1[e->prof_count % (long long)e->prof1.size()], e->stream); e->prof_count++; }
+    if (e->prof_this) { cudaEventRecord(e->prof1[e->prof_count % (long long)e->prof1.size()], e->stream); e->prof_count++; }
 }
 
 static int validate(sp_engine *e, const sp_request *rq, bool shard, double *sample_count, double *stride)
@@ -711,8 +719,10 @@ static int prepare(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, boo
         j.d_c = (unsigned long long *)e->hist.p + SP_CB_HIST_SIZE;
         j.d_gmin = (uint8_t *)e->gauges.p; j.d_gmax = j.d_gmin + W; j.d_gamp = j.d_gmax + W;
     }
-    p.cb_hist = j.d_cb;
-    p.c_hist = j.d_c;
+    // the kernels accumulate into engine-owned counters; finalize_kernel copies them to the reply (j.d_cb / j.d_c) and zeroes them
+    if ((rc = ensure(e, e->acc, 8 * (size_t)(SP_CB_HIST_SIZE + SP_MAX_CMAP))) || (rc = ensure(e, e->jhtab, 8 * (size_t)sp::JH_BINS))) return rc;
+    p.cb_hist = (unsigned long long *)e->acc.p;
+    p.c_hist = (unsigned long long *)e->acc.p + SP_CB_HIST_SIZE;
     j.d_stats = (out_dev && rp->minmax_dev) ? rp->minmax_dev : (double *)e->stats.p;
     e->stats_src = j.d_stats;
     p.db_out = want_db ? db_dev : nullptr;
@@ -958,9 +968,23 @@ static int launch_rc_kernel(sp_engine *e, rc_fn fn, int log2n, Params &q, long l
 static int enqueue_begin(sp_engine *e, Job &j)
 {
     e->launches = 0;
+    if (e->acc_dirty) {
+        // first render, or the previous one was abandoned before finalize_kernel could clean up: zero every accumulator once
+        const unsigned mm0[4] = { 0x80000000u /* f2ord(0.0f) */, 0x3cb7ffffu /* f2ord(-200.0f) */, 0u, 0u };
+        CU(cudaMemsetAsync(e->acc.p, 0, 8 * (size_t)(SP_CB_HIST_SIZE + SP_MAX_CMAP), e->stream));
+        CU(cudaMemsetAsync(e->jhist.p, 0, 8 * (size_t)sp::JH_SIZE, e->stream));
+        CU(cudaMemcpyAsync(e->mm.p, mm0, 16, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaStreamSynchronize(e->stream));                 // (mm0 lives on this stack frame)
+    }
+    e->acc_dirty = true;                                      // until finalize_kernel of THIS render has been enqueued
+    // decode table of the joint histogram: rebuilt only when the dB / colour constants change
+    const float key[5] = { j.p.jA, j.p.jB, j.p.jC, j.p.jD, (float)j.p.cmap_len };
+    if (memcmp(key, e->jhtab_key, sizeof key)) {
+        sp::jh_table_kernel<<<(sp::JH_BINS + 255) / 256, 256, 0, e->stream>>>(sp::jh_const(j.p), j.p.cmap_len - 1, (int2 *)e->jhtab.p);
+        memcpy(e->jhtab_key, key, sizeof key);
+        e->launches++;
+    }
     CU(cudaEventRecord(e->ev0, e->stream));
-    sp::prep_kernel<<<(SP_MAX_CMAP + 255) / 256, 256, 0, e->stream>>>(j.d_cb, j.d_c, j.p.cmap_len, (unsigned *)e->mm.p, (unsigned long long *)e->jhist.p);
-    e->launches++;
     return SP_OK;
 }
 
@@ -1096,9 +1120,11 @@ static int enqueue_end(sp_engine *e, Job &j)
     Params &p = j.p;
     sp::finalize_kernel<<<(unsigned)((p.nframes + 255) / 256), 256, 0, e->stream>>>(
         p.fmin, p.fmax, p.fmid, p.nframes, j.range, j.gain, j.plan.sub_r > 1 ? 1 : 0, j.d_gmin, j.d_gmax, j.d_gamp,
-        (unsigned *)e->mm.p, j.d_stats, (const unsigned long long *)e->jhist.p, sp::jh_const(p), p.cmap_len, j.d_cb, j.d_c);
+        (unsigned *)e->mm.p, j.d_stats, (unsigned long long *)e->jhist.p, (const int2 *)e->jhtab.p, p.cmap_len,
+        (unsigned long long *)e->acc.p, (unsigned long long *)e->acc.p + SP_CB_HIST_SIZE, j.d_cb, j.d_c);
     e->launches++;
     CU(cudaGetLastError());
+    e->acc_dirty = false;
     CU(cudaEventRecord(e->ev1, e->stream));
     return SP_OK;
 }
@@ -1503,6 +1529,8 @@ extern "C" int sp_profile_enable(sp_engine *e, int slots)
 {
     e = dev0(e);
     if (!e) return SP_E_INVAL;
+    e->prof_every = 1;
+    e->prof_seq = 0;
     CU(cudaSetDevice(e->dev));
     for (auto ev : e->prof0) cudaEventDestroy(ev);
     for (auto ev : e->prof1) cudaEventDestroy(ev);
@@ -1512,6 +1540,14 @@ extern "C" int sp_profile_enable(sp_engine *e, int slots)
         CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
         e->prof0.push_back(a); e->prof1.push_back(b);
     }
+    return SP_OK;
+}
+extern "C" int sp_profile_sample(sp_engine *e, int every)
+{
+    e = dev0(e);
+    if (!e || every < 1) return SP_E_INVAL;
+    e->prof_every = every;
+    e->prof_seq = 0;
     return SP_OK;
 }
 extern "C" int sp_profile_read(sp_engine *e, float *ms, int max)

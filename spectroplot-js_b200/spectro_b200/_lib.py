@@ -34,7 +34,7 @@ SYMBOLS = ["sp_abi_version", "sp_format_from_name", "sp_format_name", "sp_sample
            "sp_render_finish", "sp_render_zooms", "sp_decode", "sp_render_db", "sp_device_alloc", "sp_device_free", "sp_memcpy_h2d",
            "sp_memcpy_d2h", "sp_host_alloc_pinned", "sp_host_free_pinned", "sp_device_sync", "sp_synth_fill",
            "sp_synth_lut", "sp_device_count", "sp_sm_count", "sp_kernel_plan", "sp_profile_enable", "sp_profile_read",
-           "sp_render_shards", "sp_select_device", "sp_build_id"]
+           "sp_render_shards", "sp_select_device", "sp_build_id", "sp_profile_sample"]
 
 
 class SpError(RuntimeError):
@@ -104,6 +104,7 @@ def load():
     lib.sp_format_from_name.argtypes = [C.c_char_p]
     lib.sp_profile_enable.argtypes = [C.c_void_p, C.c_int]
     lib.sp_profile_read.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.sp_profile_sample.argtypes = [C.c_void_p, C.c_int]
     lib.sp_device_count.argtypes = [C.c_void_p]
     lib.sp_sm_count.argtypes = [C.c_void_p]
     _lib = lib
@@ -216,6 +217,10 @@ class Engine:
 
     def profile_enable(self, slots: int):
         self._check(self.lib.sp_profile_enable(self.h, int(slots)))
+
+    def profile_sample(self, every: int):
+        """Bracket only every `every`-th render-kernel launch with events."""
+        self._check(self.lib.sp_profile_sample(self.h, int(every)))
 
     def profile_read(self, max_n: int = 4096) -> np.ndarray:
         out = np.zeros(max_n, np.float32)
