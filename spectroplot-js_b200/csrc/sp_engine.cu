@@ -904,7 +904,7 @@ static int get_w_table(sp_engine *e, int n, int P, const float2 **out)
 // Frames [0, *nfast) of the chunk go through render_w_kernel (N = 64 .. 1024): whole groups of 8 frames inside the buffer.
 static int launch_w_kernel(sp_engine *e, rc_fn fn, int log2n, Params &q, long long *nfast)
 {
-    const int n = 1 << log2n, P = log2n <= 6 ? 8 : (log2n <= 8 ? 16 : 32), T = n / P, FW = 32 / T, NW = P <= 16 ? 16 : 12, WSH = n == 64 ? 4 : 2;
+    const int n = 1 << log2n, P = log2n <= 6 ? 8 : (log2n <= 8 ? 16 : 32), T = n / P, FW = 32 / T, NW = P <= 16 ? SP_W_NW16 : SP_W_NW32, WSH = n == 64 ? 4 : 2;
     const int tile = 2 * NW * WSH * FW;
     long long nf = q.chunk_frames / 8 * 8;                 // the last tile may be partial (a multiple of 8 frames)
     const long long sw = sp::sample_width(q.format);

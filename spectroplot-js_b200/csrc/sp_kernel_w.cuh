@@ -4,10 +4,10 @@
 // A warp transforms FW = 32 / T frames at a time; a thread holds P complex points (P = 8, 16 or 32, T <= P):
 //   pass A   dft<P> over the slow input digit (stride T), twiddle W_N^{t k0};
 //   exchange ONE trip through a per-warp shared-memory buffer, fenced by __syncwarp only - no block or named barrier
-//            anywhere in the transform, so the 12 - 16 FFT warps of a CTA drift freely and cover each other's latencies
+//            anywhere in the transform, so the 8 - 16 FFT warps of a CTA drift freely and cover each other's latencies
 //            (render_rc_kernel holds 64 points per thread: 232 registers, 8 warps, three named barriers per frame);
 //   pass B   P / T transforms dft<T> per thread: thread u owns rows k0 = u + T q, bins k0 + P k1.
-// The window coefficients of a thread (and for P <= 16 its twiddles) never change, so they live in registers.
+// The window coefficients and the twiddles of a thread never change, so they live in registers.
 // The raw bytes of the warp's next FW frames are prefetched by TMA bulk copies into the warp's exchange buffer; when the
 // frames overlap (hop < N, the reference's normal operating point: width ~3000 frames over a short capture) the whole
 // span is copied ONCE and every frame decodes from its own offset, i.e. the overlapping samples are re-read from shared
@@ -22,13 +22,31 @@
 #pragma once
 #include "sp_kernel_r64.cuh"
 
+// tuning knobs (A/B builds, profiles/r02_w_kernel_tuning.txt): FFT warps per CTA for P <= 16 / P = 32 (multiples of 4: setmaxnreg
+// works on warpgroups) and whether the P = 32 twiddles live in registers (8 warps x 232 registers: adopted, +4 % at N = 512) or in
+// shared memory (12 warps x 152 registers)
+#ifndef SP_W_NW16
+#define SP_W_NW16 16
+#endif
+#ifndef SP_W_NW32
+#define SP_W_NW32 8
+#endif
+#ifndef SP_W_TWREG32
+#define SP_W_TWREG32 1
+#endif
+
 namespace sp {
 
 template <int LOG2P, int LOG2T, int FMT> struct WCfg {
     static constexpr int P = 1 << LOG2P, T = 1 << LOG2T, N = P * T, FW = 32 / T, Q = P / T;
-    static constexpr int NW = P <= 16 ? 16 : 12;                                 // FFT warps
+    static constexpr int NW = P <= 16 ? SP_W_NW16 : SP_W_NW32;                   // FFT warps
+    static_assert(NW % 4 == 0, "setmaxnreg is a warpgroup (4 warps) operation: the FFT warps must fill whole warpgroups (a mixed one hangs)");
     static constexpr int FFT_THREADS = 32 * NW, STORE_THREADS = 128, THREADS = FFT_THREADS + STORE_THREADS;
-    static constexpr int FFT_REGS = P <= 16 ? 104 : 152, STORE_REGS = 40;        // 512 x 104 + 128 x 40 <= 640 x 96;  384 x 152 + 128 x 40 <= 512 x 128
+    static constexpr int STORE_REGS = 40;
+    // registers: the CTA's allocation at launch is THREADS x (65536 / THREADS rounded down to 8); setmaxnreg moves registers inside it
+    static constexpr int LAUNCH_REGS = (65536 / THREADS) / 8 * 8 > 255 ? 248 : (65536 / THREADS) / 8 * 8;
+    static constexpr int FFT_REGS_RAW = (THREADS * LAUNCH_REGS - STORE_THREADS * STORE_REGS) / FFT_THREADS / 8 * 8;
+    static constexpr int FFT_REGS = FFT_REGS_RAW > 232 ? 232 : FFT_REGS_RAW;
     static constexpr int WSH = N == 64 ? 4 : 2;                                  // warp-steps per warp and staging half
     static constexpr int HF = NW * WSH * FW, F = 2 * HF;                         // frames per staging half / tile
     static constexpr int SWB = sample_width(FMT == FMT_RUNTIME ? CF64 : FMT);
@@ -43,7 +61,7 @@ template <int LOG2P, int LOG2T, int FMT> struct WCfg {
     static constexpr int XBYTES = ((FW * FSTR * 8 > FW * RAWP ? FW * FSTR * 8 : FW * RAWP) + 15) & ~15;
     static constexpr int FPITCH = (HF + 31) / 32 * 32 + FW;                      // staging words per word column: STS.32 of a warp conflict-free
     static constexpr int HALF_WORDS = (N / 4) * FPITCH;
-    static constexpr bool TW_SMEM = P > 16;                                      // twiddles from shared memory (31 per thread do not fit the registers)
+    static constexpr bool TW_SMEM = P > 16 && !SP_W_TWREG32;                     // twiddles from shared memory (31 per thread do not fit 152 registers)
     static constexpr size_t SMEM_BYTES = (size_t)NW * XBYTES + (size_t)2 * HALF_WORDS * 4 + (size_t)JH_SIZE * 4 + (TW_SMEM ? (size_t)T * 32 * 8 : 0)
                                        + 1024 /* LUT */ + (size_t)F * 8 /* s_mm */ + (size_t)NW * 2 * FW * 4 /* s_off */ + (size_t)NW * 8 + 64
                                        + 128 + 1024 /* LUT alignment */;
