@@ -213,10 +213,8 @@ extern "C" cudaError_t SP_CAT(sp_r64_, SP_INST_TAG)(int sub, const sp::Params *p
 }
 extern "C" cudaError_t SP_CAT(sp_rc_, SP_INST_TAG)(int log2n, const sp::Params *p, int grid, cudaStream_t st, const float2 *tw14, int *occ_out)
 {
+    // N = 2048 only: render_w_kernel took over N = 256 .. 1024 in round 2 (both layouts); the template still covers C = 4 .. 32
     switch (log2n) {
-    case 8: return sp::launch_rc_v<2, SP_INST_FMT>(*p, grid, st, tw14, occ_out);
-    case 9: return sp::launch_rc_v<3, SP_INST_FMT>(*p, grid, st, tw14, occ_out);
-    case 10: return sp::launch_rc_v<4, SP_INST_FMT>(*p, grid, st, tw14, occ_out);
     case 11: return sp::launch_rc_v<5, SP_INST_FMT>(*p, grid, st, tw14, occ_out);
     default: return cudaErrorInvalidValue;
     }

@@ -16,8 +16,8 @@
 // with full / empty mbarriers and setmaxnreg: as in render_r64_kernel.  The staging tile is transposed ([word][frame]),
 // so a store warp reads 8 frames of a word with vector loads and its lanes cover 8-frame groups that are adjacent in the
 // image row: a row receives 256 B .. 1 KB of contiguous bytes per store instruction.
-// Spectrogram layout, cmap_len <= 256, whole groups of 8 frames inside the buffer; everything else stays on
-// render_rc_kernel / render_kernel.  Replaces the hot loops of reference lib/worker.js:68-137 (+ lib/samples.js:313-400,
+// Spectrogram and waterfall layout, cmap_len <= 256, whole groups of 8 frames inside the buffer; everything else (split-real,
+// dB tap, longer colormaps, remainder frames) stays on render_rc_kernel / render_kernel.  Replaces the hot loops of reference lib/worker.js:68-137 (+ lib/samples.js:313-400,
 // lib/fft_nayuki.js:54-96).
 #pragma once
 #include "sp_kernel_r64.cuh"
@@ -165,8 +165,24 @@ __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_
                 mbar_wait(s_full + h, kk & 1);
                 const size_t x0 = (size_t)(p.chunk_first + xr0) + HF * h;
                 const unsigned *half = s_stage + h * B::HALF_WORDS;
+                if (p.waterfall) {
+                    // waterfall layout (lib/worker.js:116): frame x is image row nframes - 1 - x, bin b is column (b + n/2 - 1) mod n.
+                    // Item = (frame, word column): the T lanes that share (q, m) hold T consecutive bins, i.e. T consecutive
+                    // columns - every store instruction writes runs of 4 T contiguous bytes; the staged words of those lanes are
+                    // FPITCH apart (conflict-free, like the FFT warps' writes).
 #pragma unroll 1
-                for (int id = ht; id < (N / 4) * G8; id += B::STORE_THREADS) {
+                    for (int id = ht; id < HF * (N / 4); id += B::STORE_THREADS) {
+                        const int wcol = id % (N / 4), fl = id / (N / 4);
+                        if (xr0 + HF * h + fl >= p.chunk_frames) break;                   // partial last tile
+                        const int u = wcol % T, qm = wcol / T, m = qm % (T / 4), q = qm / (T / 4);
+                        const unsigned w = half[wcol * B::FPITCH + fl];
+                        uint32_t *rowp = reinterpret_cast<uint32_t *>(p.image) + (size_t)N * (size_t)(p.nframes - 1 - (long long)(x0 + fl));
+#pragma unroll
+                        for (int j = 0; j < 4; j++) rowp[((u + T * q) + P * (4 * m + j) + N / 2 - 1) & (N - 1)] = lut_at(lut_base, w, j);
+                    }
+                }
+#pragma unroll 1
+                for (int id = ht; id < (p.waterfall ? 0 : (N / 4) * G8); id += B::STORE_THREADS) {
                     // item = (word column, 8-frame group): adjacent lanes take adjacent groups of the same image rows
                     const int g = id % G8, wcol = id / G8;
                     if (xr0 + HF * h + 8 * g >= p.chunk_frames) continue;         // partial last tile (chunk_frames % 8 == 0)
