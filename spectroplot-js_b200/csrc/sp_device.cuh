@@ -466,7 +466,9 @@ template <int K0> __device__ __forceinline__ void dft64_twiddle_row(cf (&v)[64])
 }
 
 // n = 8*n1 + n0, k = k0 + 8*k1 :  W64^{nk} = W8^{n1 k0} * W64^{n0 k0} * W8^{n0 k1}; natural order in and out
-template <> __device__ __forceinline__ void dft<64>(cf (&v)[64])
+// between(): called once every input has been consumed (after the eight column transforms) - the fused kernels put the
+// barrier that releases the buffer the inputs were loaded from there, so that the loads overlap the column transforms
+template <class Between> __device__ __forceinline__ void dft64_between(cf (&v)[64], Between between)
 {
 #pragma unroll
     for (int n0 = 0; n0 < 8; n0++) {                       // DFT-8 over n1 of column n0; result k0 -> v[8*k0 + n0]
@@ -477,6 +479,7 @@ template <> __device__ __forceinline__ void dft<64>(cf (&v)[64])
 #pragma unroll
         for (int k0 = 0; k0 < 8; k0++) v[8 * k0 + n0] = u[k0];
     }
+    between();
     dft64_twiddle_row<1>(v); dft64_twiddle_row<2>(v); dft64_twiddle_row<3>(v); dft64_twiddle_row<4>(v);
     dft64_twiddle_row<5>(v); dft64_twiddle_row<6>(v); dft64_twiddle_row<7>(v);
     cf y[64];
@@ -492,6 +495,7 @@ template <> __device__ __forceinline__ void dft<64>(cf (&v)[64])
 #pragma unroll
     for (int i = 0; i < 64; i++) v[i] = y[i];
 }
+template <> __device__ __forceinline__ void dft<64>(cf (&v)[64]) { dft64_between(v, [] {}); }
 
 // 32-point DFT in registers: n = 8*n1 + n0 (n1 < 4), k = k0 + 4*k1 :  W32^{nk} = W4^{n1 k0} * W32^{n0 k0} * W8^{n0 k1}
 template <int K0> __device__ __forceinline__ void dft32_twiddle_row(cf (&v)[32])

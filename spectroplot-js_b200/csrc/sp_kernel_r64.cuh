@@ -26,9 +26,6 @@
 #pragma once
 #include "sp_prims.cuh"
 
-#ifndef SP_R64_ONEDFT
-#define SP_R64_ONEDFT 0        // measured: the two-trip loop is 5 % SLOWER (0.298 vs 0.283 ms, profiles/r02_ab_r64.txt): the scheduling barrier costs more than the smaller loop body saves
-#endif
 #ifndef SP_XP
 #define SP_XP 0             // timing-only experiment switches (wrong output): 1 conflict-free histogram addresses, 2 no histogram atomics,
 #endif                      // 4 no window, 8 no product twiddles, 16 no log2 / joint index
@@ -298,92 +295,83 @@ __global__ void __launch_bounds__(384, 1) render_r64_kernel(const Params p, cons
             // produced a misaligned mbarrier address)
             asm volatile("" : "+r"(half));
             cf v[64];
-            // ONE copy of the 64-point transform in the instruction stream: the frame step is a two-trip loop around it
-            // (trip 0: load + pass A + exchange, trip 1: pass B + epilogue), which takes 7 KB of SASS out of the loop body
-            // (43 KB -> 38 KB against a 32 KB instruction cache shared by four streams in different phases).
-            // SP_R64_ONEDFT=0 unrolls the two trips again (the round-1 instruction stream).
-#if SP_R64_ONEDFT
-            int npass = 2;
-            asm volatile("" : "+r"(npass));
-#else
-            constexpr int npass = 2;
-#endif
             const bool split = OPT && !SUB && p.channel_mode;           // split-real needs the buffer once more, see below
             auto prefetch = [&]() {
                 if (step < B::STEPS - 1) stage(xr0 + fl + B::STREAMS, k0sub, fpar);
                 else if (next_tile < p.ntiles) stage(tile_xr0(next_tile) + s, SUB ? (int)(next_tile % sub_r) : 0, fpar);
             };
-#if SP_R64_ONEDFT
-#pragma unroll 1
-#else
+            // ---------------- load + decode + window (lib/worker.js:70-75) ----------------
+            // in the order the column transforms of pass A consume them (columns 0..3 need the even window quads, 4..7 the
+            // odd ones), so that the first transforms start while the later loads are still in flight
+            mbar_wait(mbar, fpar);
+            if constexpr (SUB) {
 #pragma unroll
-#endif
-            for (int pass = 0; pass < npass; pass++) {
-                if (pass == 0) {
-                    // ---------------- load + decode + window (lib/worker.js:70-75) ----------------
-                    mbar_wait(mbar, fpar);
-                    if constexpr (SUB) {
+                for (int n0 = 0; n0 < 8; n0++)
 #pragma unroll
-                        for (int a = 0; a < 64; a++) v[a] = cld(reinterpret_cast<const float2 *>(raw) + T * a + t);
-                    } else {
-                        const unsigned char *rp = raw + s_off[s * 2 + fpar];
+                    for (int n1 = 0; n1 < 8; n1++) v[8 * n1 + n0] = cld(reinterpret_cast<const float2 *>(raw) + T * (8 * n1 + n0) + t);
+            } else {
+                const unsigned char *rp = raw + s_off[s * 2 + fpar];
+                const float4 *wrow = B::TMA ? p.window_t + t : reinterpret_cast<const float4 *>(s_win + t * B::WIN_PITCH);
 #pragma unroll
-                        for (int a = 0; a < 64; a++) v[a] = decode_raw_cf<FMT>(rp, T * a + t, p.format);
-                        // raw sample at p0 + n/2 (lib/worker.js:131-133); the power-of-two scale is exact
-                        if (t == 0 && valid) p.fmid[p.chunk_first + xr0 + fl] = make_float2(cre(v[32]) * raw_scale<FMT>(), cim(v[32]) * raw_scale<FMT>());
-                        const float4 *wrow = B::TMA ? p.window_t + t : reinterpret_cast<const float4 *>(s_win + t * B::WIN_PITCH);
+                for (int qq = 0; qq < 16; qq++) {
+                    const int q = 2 * (qq & 7) + (qq >> 3);
+                    const float4 w = (SP_XP & 4) ? make_float4(1.f, 1.f, 1.f, 1.f) : B::TMA ? __ldg(wrow + 64 * q) : wrow[(q + t) & 15];
+                    cf d[4];
 #pragma unroll
-                        for (int q = 0; q < 16; q++) {
-                            const float4 w = (SP_XP & 4) ? make_float4(1.f, 1.f, 1.f, 1.f) : B::TMA ? __ldg(wrow + 64 * q) : wrow[(q + t) & 15];
-                            v[4 * q] = cscale(v[4 * q], w.x);         v[4 * q + 1] = cscale(v[4 * q + 1], w.y);
-                            v[4 * q + 2] = cscale(v[4 * q + 2], w.z); v[4 * q + 3] = cscale(v[4 * q + 3], w.w);
-                        }
-                    }
-                    fpar ^= 1;
-
+                    for (int c = 0; c < 4; c++) d[c] = decode_raw_cf<FMT>(rp, T * (4 * q + c) + t, p.format);
+                    // raw sample at p0 + n/2 (lib/worker.js:131-133); the power-of-two scale is exact
+                    if (q == 8 && t == 0 && valid) p.fmid[p.chunk_first + xr0 + fl] = make_float2(cre(d[0]) * raw_scale<FMT>(), cim(d[0]) * raw_scale<FMT>());
+                    v[4 * q] = cscale(d[0], w.x);     v[4 * q + 1] = cscale(d[1], w.y);
+                    v[4 * q + 2] = cscale(d[2], w.z); v[4 * q + 3] = cscale(d[3], w.w);
                 }
-                dft<64>(v);                                             // pass A over the slow input digit / pass B: v[k1] is bin t + 64*k1
-                if (pass == 0) {
-                    {
-                        const float4 *twp = reinterpret_cast<const float4 *>(s_tw + t * B::TW_PITCH);
-                        float2 w[8];                                            // w[j] = W^{t*j}, j = 1..7
-                        {
-                            const float4 a = twp[0], b = twp[1], c = twp[2], d = twp[3];
-                            w[1] = make_float2(a.x, a.y); w[2] = make_float2(a.z, a.w); w[3] = make_float2(b.x, b.y); w[4] = make_float2(b.z, b.w);
-                            w[5] = make_float2(c.x, c.y); w[6] = make_float2(c.z, c.w); w[7] = make_float2(d.x, d.y);
+            }
+            fpar ^= 1;
+            // ---------------- pass A: DFT-64 over the slow input digit; the raw frame is released between its two stages ----------------
+            dft64_between(v, [&] { stream_barrier(s); });
+            {
+                // twiddles W^{t*k}, each product followed by its exchange store Z[k0][t] (the stores ride between the FFMA2)
+                const float4 *twp = reinterpret_cast<const float4 *>(s_tw + t * B::TW_PITCH);
+                float2 w[8];                                            // w[j] = W^{t*j}, j = 1..7
+                const float4 a = twp[0], b = twp[1], c = twp[2], d = twp[3];
+                w[1] = make_float2(a.x, a.y); w[2] = make_float2(a.z, a.w); w[3] = make_float2(b.x, b.y); w[4] = make_float2(b.z, b.w);
+                w[5] = make_float2(c.x, c.y); w[6] = make_float2(c.z, c.w); w[7] = make_float2(d.x, d.y);
 #pragma unroll
-                            for (int j = 1; j < 8; j++) v[j] = cmul(v[j], w[j]);
-                            float2 hi[8];                                       // hi[i] = W^{t*8i}, i = 1..7
-                            hi[1] = make_float2(d.z, d.w);
-                            const float4 e = twp[4], f = twp[5], g = twp[6];
-                            hi[2] = make_float2(e.x, e.y); hi[3] = make_float2(e.z, e.w); hi[4] = make_float2(f.x, f.y);
-                            hi[5] = make_float2(f.z, f.w); hi[6] = make_float2(g.x, g.y); hi[7] = make_float2(g.z, g.w);
+                for (int j = 1; j < 8; j++) v[j] = cmul(v[j], w[j]);
 #pragma unroll
-                            for (int i = 1; i < 8; i++) {
-                                v[8 * i] = cmul(v[8 * i], hi[i]);
+                for (int j = 0; j < 8; j++) cst(X + j * B::XP + t, v[j]);
+                float2 hi[8];                                           // hi[i] = W^{t*8i}, i = 1..7
+                hi[1] = make_float2(d.z, d.w);
+                const float4 e = twp[4], f = twp[5], g = twp[6];
+                hi[2] = make_float2(e.x, e.y); hi[3] = make_float2(e.z, e.w); hi[4] = make_float2(f.x, f.y);
+                hi[5] = make_float2(f.z, f.w); hi[6] = make_float2(g.x, g.y); hi[7] = make_float2(g.z, g.w);
 #pragma unroll
-                                for (int j = 1; j < 8; j++) v[8 * i + j] = cmul(v[8 * i + j], (SP_XP & 8) ? w[j] : cun(cmul(cpk(hi[i]), w[j])));
-                            }
-                        }
-                    }
-                    stream_barrier(s);                                          // every thread of the stream has consumed the raw frame
+                for (int i = 1; i < 8; i++) {
+                    v[8 * i] = cmul(v[8 * i], hi[i]);
 #pragma unroll
-                    for (int k = 0; k < 64; k++) cst(X + k * B::XP + t, v[k]);  // Z[k0][t]
-                    stream_barrier(s);
-                    // ---------------- pass B: thread k0 = t, DFT-64 over b ----------------
-                    {
-                        const float4 *row = reinterpret_cast<const float4 *>(X + t * B::XP);
+                    for (int j = 1; j < 8; j++) v[8 * i + j] = cmul(v[8 * i + j], (SP_XP & 8) ? w[j] : cun(cmul(cpk(hi[i]), w[j])));
 #pragma unroll
-                        for (int m = 0; m < 32; m++) {
-                            const float4 q = row[m];
-                            v[2 * m] = cpk(q.x, q.y); v[2 * m + 1] = cpk(q.z, q.w);
-                        }
-                    }
-                    stream_barrier(s);                                          // the exchange buffer is free: prefetch the stream's next frame
-                    if (t == 0 && !split) prefetch();
-                    // first frame of this stream in staging half step/2: the store warps must be done with the half (previous tile)
-                    if ((step & 1) == 0) mbar_wait(s_empty + half, (kk + 1) & 1);
-                } else {
+                    for (int j = 0; j < 8; j++) cst(X + (8 * i + j) * B::XP + t, v[8 * i + j]);
+                }
+            }
+            stream_barrier(s);
+            // ---------------- pass B: thread k0 = t, DFT-64 over b; v[k1] is bin t + 64*k1 ----------------
+            {
+                const float4 *row = reinterpret_cast<const float4 *>(X + t * B::XP);
+#pragma unroll
+                for (int mm = 0; mm < 32; mm++) {                       // columns (0, 1) first, then (2, 3), ...
+                    const int m = 4 * (mm & 7) + (mm >> 3);
+                    const float4 q = row[m];
+                    v[2 * m] = cpk(q.x, q.y); v[2 * m + 1] = cpk(q.z, q.w);
+                }
+            }
+            dft64_between(v, [&] {
+                stream_barrier(s);                                      // the exchange buffer is free: prefetch the stream's next frame
+                if (t == 0 && !split) prefetch();
+            });
+            // first frame of this stream in staging half step/2: the store warps must be done with the half (previous tile)
+            if ((step & 1) == 0) mbar_wait(s_empty + half, (kk + 1) & 1);
+            {
+                {
                     if constexpr (OPT && !SUB) {
                         if (split) {
                             // ---------------- split-real post-process (lib/fft_nayuki.js:103-119) ----------------
