@@ -381,8 +381,9 @@ __global__ void __launch_bounds__(384, 1) render_big_kernel(const Params p, cons
                 for (int a = 0; a < 64; a++) { const float2 q = __ldcg(src + T * a + t); v[a] = cpk(q.x, q.y); }
 
                 // ---------------- pass A: DFT-64 over the slow input digit, twiddle W_4096^{t*k0} ----------------
-                dft<64>(v);
+                dft64_between(v, [&] { stream_barrier(s); });               // the previous frame's rows have been read back
                 {
+                    // the exchange stores Z[k0][t] ride between the twiddle products (see render_r64_kernel)
                     const float4 *twp = reinterpret_cast<const float4 *>(s_tw + t * B::TW_PITCH);
                     float2 w[8];                                            // w[j] = W^{t*j}, j = 1..7
                     const float4 a = twp[0], b = twp[1], c = twp[2], d = twp[3];
@@ -390,6 +391,8 @@ __global__ void __launch_bounds__(384, 1) render_big_kernel(const Params p, cons
                     w[5] = make_float2(c.x, c.y); w[6] = make_float2(c.z, c.w); w[7] = make_float2(d.x, d.y);
 #pragma unroll
                     for (int j = 1; j < 8; j++) v[j] = cmul(v[j], w[j]);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) cst(X + k * B::XP + t, v[k]);
                     float2 hi[8];                                           // hi[i] = W^{t*8i}, i = 1..7
                     hi[1] = make_float2(d.z, d.w);
                     const float4 e = twp[4], f = twp[5], gq = twp[6];
@@ -400,11 +403,10 @@ __global__ void __launch_bounds__(384, 1) render_big_kernel(const Params p, cons
                         v[8 * i] = cmul(v[8 * i], hi[i]);
 #pragma unroll
                         for (int j = 1; j < 8; j++) v[8 * i + j] = cmul(v[8 * i + j], cun(cmul(cpk(hi[i]), w[j])));
+#pragma unroll
+                        for (int k = 8 * i; k < 8 * i + 8; k++) cst(X + k * B::XP + t, v[k]);
                     }
                 }
-                stream_barrier(s);                                          // the previous frame's rows have been read back
-#pragma unroll
-                for (int k = 0; k < 64; k++) cst(X + k * B::XP + t, v[k]);  // Z[k0][t]
                 stream_barrier(s);
                 // ---------------- pass B: thread k0 = t, DFT-64 over b ----------------
                 {

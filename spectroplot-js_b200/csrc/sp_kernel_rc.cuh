@@ -212,8 +212,10 @@ __global__ void __launch_bounds__(384, 1) render_rc_kernel(const Params p, const
             fpar ^= 1;
 
             // ---------------- pass A: DFT-64 over the slow input digit, twiddle W_N^{t*k0} ----------------
-            dft<64>(v);
+            dft64_between(v, [&] { stream_barrier(s); });               // every thread of the stream has consumed its raw frame
             {
+                // each twiddled row goes straight to the 64-point chunk k0 / RPT (owner thread) at (k0 % RPT) * C + t: the
+                // exchange stores ride between the twiddle products (see render_r64_kernel)
                 const float4 *twp = reinterpret_cast<const float4 *>(s_tw + t * B::TW_PITCH);
                 float2 w[8], hi[8];                                     // w[j] = W^{t*j}, hi[i] = W^{t*8i}
                 const float4 a = twp[0], b = twp[1], c = twp[2], d = twp[3], e = twp[4], f = twp[5], g = twp[6];
@@ -224,16 +226,16 @@ __global__ void __launch_bounds__(384, 1) render_rc_kernel(const Params p, const
 #pragma unroll
                 for (int j = 1; j < 8; j++) v[j] = cmul(v[j], w[j]);
 #pragma unroll
+                for (int k = 0; k < 8; k++) cst(X + (k / RPT) * B::XP + (k % RPT) * C + t, v[k]);
+#pragma unroll
                 for (int i = 1; i < 8; i++) {
                     v[8 * i] = cmul(v[8 * i], hi[i]);
 #pragma unroll
                     for (int j = 1; j < 8; j++) v[8 * i + j] = cmul(v[8 * i + j], cun(cmul(cpk(hi[i]), w[j])));
+#pragma unroll
+                    for (int k = 8 * i; k < 8 * i + 8; k++) cst(X + (k / RPT) * B::XP + (k % RPT) * C + t, v[k]);
                 }
             }
-            stream_barrier(s);                                          // every thread of the stream has consumed its raw frame
-            // row k0 goes to the 64-point chunk k0 / RPT (owner thread) at (k0 % RPT) * C + t
-#pragma unroll
-            for (int k = 0; k < 64; k++) cst(X + (k / RPT) * B::XP + (k % RPT) * C + t, v[k]);
             stream_barrier(s);
             // ---------------- pass B: thread t owns rows t*RPT .. t*RPT + RPT - 1: RPT transforms of length C ----------------
             {
