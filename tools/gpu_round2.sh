@@ -13,7 +13,7 @@ timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k re
     python bench.py --steps 2 --warmup 3 --no-cpu --no-configs > $OUT/ncu_full_r64_$TAG.log 2>&1
 timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k regex:render_w_ -s 3 -c 1 -f -o $OUT/prof_w_$TAG \
     python tools/sweep.py X:CS16:512:1:26 1 > $OUT/ncu_full_w_$TAG.log 2>&1
-timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k regex:render_big -s 3 -c 1 -f -o $OUT/prof_big_$TAG \
+SP_FOURSTEP=ring timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k regex:render_big -s 3 -c 1 -f -o $OUT/prof_big_$TAG \
     python tools/sweep.py C5 1 > $OUT/ncu_full_big_$TAG.log 2>&1
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sectors_op_read.sum,lts__t_sector_op_read_hit_rate.pct,l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum,smsp__inst_executed.sum
 for dbg in 0 16; do
