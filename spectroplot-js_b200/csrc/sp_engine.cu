@@ -490,10 +490,10 @@ extern "C" const char *sp_kernel_plan(sp_engine *e, int format, int n, int chann
     else if (pl.log2k == 12 && pl.sub_r == 1 && fast_ok && r64_for(format))
         o += snprintf(buf + o, sizeof buf - o, "render_r64_kernel<%s> (64x64 FFT, one exchange, 4 frame streams + store warpgroup, TMA-staged input, joint histogram, "
                       "RGBA tiles + tensor-TMA row stores%s) | ", fname, channel_mode ? ", split-real in the FFT warps" : "");
-    else if (pl.log2k >= 6 && pl.log2k <= 10 && !channel_mode && fast_ok && w_for(format))
+    else if (pl.log2k >= 6 && pl.log2k <= 10 && fast_ok && w_for(format))
         o += snprintf(buf + o, sizeof buf - o, "render_w_kernel<%s, N=%dx%d> (warp-synchronous, one exchange, span-staged input, tables in registers, joint histogram, "
-                      "store warpgroup, spectrogram and waterfall layout) | ", fname, pl.log2k <= 6 ? 8 : (pl.log2k <= 8 ? 16 : 32),
-                      (1 << pl.log2k) / (pl.log2k <= 6 ? 8 : (pl.log2k <= 8 ? 16 : 32)));
+                      "store warpgroup, spectrogram and waterfall layout%s) | ", fname, pl.log2k <= 6 ? 8 : (pl.log2k <= 8 ? 16 : 32),
+                      (1 << pl.log2k) / (pl.log2k <= 6 ? 8 : (pl.log2k <= 8 ? 16 : 32)), channel_mode ? ", split-real in the FFT warps" : "");
     else if (pl.log2k == 11 && !channel_mode && fast_ok && rc_for(format))
         o += snprintf(buf + o, sizeof buf - o, "render_rc_kernel<%s, N=64x%d> (one exchange, joint histogram, TMA-staged input, store warpgroup) | ", fname, (1 << pl.log2k) / 64);
     snprintf(buf + o, sizeof buf - o, "%s%srender_kernel<N=%d,%s> tile=%d frames%s (every option; remainder frames, ragged ends, dB tap, cmap_len > 256)",
@@ -1005,7 +1005,7 @@ static int enqueue_frames(sp_engine *e, Job &j, Params &p)
         }
         // N = 64 .. 1024, spectrogram layout: the warp-synchronous kernel (SP_W_MAX: largest log2 N it takes, default 10; 0 = off)
         static const int w_max = getenv("SP_W_MAX") ? atoi(getenv("SP_W_MAX")) : 10;
-        if (j.plan.log2k >= 6 && j.plan.log2k <= w_max && j.plan.log2k <= 10 && fused_eligible(p, /* waterfall rows in the store warps */ true) && w_for(fmt)) {
+        if (j.plan.log2k >= 6 && j.plan.log2k <= w_max && j.plan.log2k <= 10 && fused_eligible(p, /* waterfall rows in the store warps */ true, /* split-real in the FFT warps */ true) && w_for(fmt)) {
             long long nfast = 0;
             int rc = launch_w_kernel(e, w_for(fmt), j.plan.log2k, q, &nfast);
             if (rc) return rc;

@@ -152,9 +152,10 @@ static cudaError_t launch_w_v(const Params &p, int grid, cudaStream_t st, const 
         if (occ_out) *occ_out = 0;
         return occ_out ? cudaSuccess : cudaErrorInvalidValue;
     } else {
-        auto kfn = render_w_kernel<LOG2P, LOG2T, FMT>;
-        static bool attr_flags[64] = {};
-        bool &attr_done = attr_flag(attr_flags);
+        // channelMode messages take the instantiation that carries the split-real post-process
+        auto kfn = p.channel_mode ? render_w_kernel<LOG2P, LOG2T, FMT, true> : render_w_kernel<LOG2P, LOG2T, FMT, false>;
+        static bool attr_flags[2][64] = {};
+        bool &attr_done = attr_flag(attr_flags[p.channel_mode ? 1 : 0]);
         if (!attr_done) {
             cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::SMEM_BYTES);
             if (e != cudaSuccess) return e;

@@ -16,8 +16,8 @@
 // with full / empty mbarriers and setmaxnreg: as in render_r64_kernel.  The staging tile is transposed ([word][frame]),
 // so a store warp reads 8 frames of a word with vector loads and its lanes cover 8-frame groups that are adjacent in the
 // image row: a row receives 256 B .. 1 KB of contiguous bytes per store instruction.
-// Spectrogram and waterfall layout, cmap_len <= 256, whole groups of 8 frames inside the buffer; everything else (split-real,
-// dB tap, longer colormaps, remainder frames) stays on render_rc_kernel / render_kernel.  Replaces the hot loops of reference lib/worker.js:68-137 (+ lib/samples.js:313-400,
+// Spectrogram and waterfall layout, split-real (OPT), cmap_len <= 256, whole groups of 8 frames inside the buffer; everything else
+// (dB tap, longer colormaps, remainder frames) stays on render_kernel.  Replaces the hot loops of reference lib/worker.js:68-137 (+ lib/samples.js:313-400,
 // lib/fft_nayuki.js:54-96).
 #pragma once
 #include "sp_kernel_r64.cuh"
@@ -68,7 +68,9 @@ template <int LOG2P, int LOG2T, int FMT> struct WCfg {
 };
 
 // twW: [P][T] float2 = W_N^{t*k} (k = 0 .. P-1; double -> fp32 once)
-template <int LOG2P, int LOG2T, int FMT>
+// OPT = true: the same kernel with the split-real post-process (lib/fft_nayuki.js:103-119) compiled in; the launcher takes it
+// for channelMode messages only, so the plain kernel carries neither its registers nor its code.
+template <int LOG2P, int LOG2T, int FMT, bool OPT = false>
 __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_kernel(const Params p, const float2 *__restrict__ twW)
 {
     using B = WCfg<LOG2P, LOG2T, FMT>;
@@ -295,10 +297,12 @@ __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_
                 }
             }
             __syncwarp();                                               // the exchange buffer is free: prefetch the warp's next frames
-            if (lane == 0) {
+            const bool split = OPT && p.channel_mode;                   // split-real needs the buffer once more, see below
+            auto prefetch = [&]() {
                 if (hj + 1 < 2 * B::WSH) stage(step_first(tile, (hj + 1) / B::WSH, (hj + 1) % B::WSH), fpar);
                 else if (next_tile < p.ntiles) stage(step_first(next_tile, 0, 0), fpar);
-            }
+            };
+            if (lane == 0 && !split) prefetch();
             if (j == 0) mbar_wait(s_empty + h, (kk + 1) & 1);           // the store warps are done with this staging half (previous tile)
 #pragma unroll
             for (int q = 0; q < Q; q++) {
@@ -308,6 +312,33 @@ __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_
                 dft<T>(u_);                                             // u_[k1] is bin (t + T*q) + P*k1
 #pragma unroll
                 for (int i = 0; i < T; i++) v[q * T + i] = u_[i];
+            }
+            if constexpr (OPT) {
+                if (split) {
+                    // ---------------- split-real post-process (lib/fft_nayuki.js:103-119) ----------------
+                    // bin i pairs with bin n - i, which lives in lane (T - t) mod T of the same frame: one more trip through the
+                    // frame's exchange area, this time indexed by bin (writes and reads of a warp instruction are consecutive
+                    // words: conflict-free).  Bins below n/2 are the registers k1 < T/2, bins above it k1 >= T/2; bin 0 and
+                    // bin n/2 are lane 0's registers (q = 0, k1 = 0 / T/2).
+#pragma unroll
+                    for (int r = 0; r < P; r++) cst(X + (t + T * (r / T) + P * (r % T)), v[r]);
+                    __syncwarp();
+#pragma unroll
+                    for (int r = 0; r < P; r++) {
+                        const int q = r / T, k1 = r % T;
+                        const int b = t + T * q + P * k1;
+                        const cf w = cld(X + ((N - b) & (N - 1)));
+                        const float2 fa = cun(v[r]), fb = cun(w);
+                        cf nv;
+                        if (k1 < T / 2) nv = cscale(cadd(v[r], cpk(fb.x, -fb.y)), 0.5f);                    // i < n/2:  (re_i + re_p, im_i - im_p) / 2
+                        else nv = cscale(cadd(cpk(fa.y, fa.x), cpk(fb.y, -fb.x)), 0.5f);                     // i > n/2:  (im_p + im_i, -re_p + re_i) / 2
+                        if (q == 0 && k1 == 0 && t == 0) nv = cpk(fmaf(0.0f, fa.y, fa.x), 0.0f);             // imag[0] = 0; a NaN there reaches real[0] (NaN * 0)
+                        if (q == 0 && k1 == T / 2 && t == 0) nv = cpk(0.0f, 0.0f);                           // real[n/2] = imag[0] (just zeroed), imag[n/2] = 0
+                        v[r] = nv;
+                    }
+                    __syncwarp();                                       // now the buffer is free
+                    if (lane == 0) prefetch();
+                }
             }
 
             // ---------------- per-bin epilogue (lib/worker.js:85-122) ----------------

@@ -66,7 +66,17 @@ def check_parity(gpu, ora, cmap, n, width, waterfall=False, gpu_db=None, label="
     assert int(gpu["c_hist"].sum()) == int(ora.c_hist.sum()) == width * n, label
     assert int(np.abs(gpu["c_hist"].astype(np.int64) - ora.c_hist.astype(np.int64)).sum()) <= 2 * nbad, label + ": c_hist"
     cb_d = np.abs(gpu["cB_hist"].astype(np.int64) - ora.cB_hist.astype(np.int64)).sum()
-    assert cb_d <= 2 * max(2, int(PIXEL_FRAC * diff.size)), f"{label}: cB_hist differs by {cb_d}"
+    # a pixel may sit in the neighbouring 0.1 dB bin when the reference's own value lies within 2e-4 dB of the bin edge
+    # (lib/worker.js:105: ~~(2.5 - 10 * d0)); that is 50 x tighter than the 0.01 dB bar and matters for pictures of a few
+    # thousand pixels only, where 0.1 % of the pixels is less than the handful of such ties a picture happens to hold
+    edge = 0
+    odb = getattr(ora, "db", None)
+    if odb is not None and np.size(odb) == diff.size:
+        x = 2.5 - 10.0 * np.asarray(odb, dtype=np.float64)
+        with np.errstate(invalid="ignore"):
+            fr = np.abs(x - np.round(x))
+        edge = int((fr[np.isfinite(fr)] < 2e-3).sum())
+    assert cb_d <= 2 * max(2, int(PIXEL_FRAC * diff.size), edge), f"{label}: cB_hist differs by {cb_d} (ties allowed: {edge})"
     assert abs(int(gpu["cB_hist"].sum()) - int(ora.cB_hist.sum())) <= max(2, int(PIXEL_FRAC * diff.size)), label
     # gauges: +-1 count (fp32 min/max feeding a rounding)
     for k in ("gauge_mins", "gauge_maxs", "gauge_amps"):

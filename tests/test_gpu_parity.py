@@ -805,6 +805,20 @@ def test_waterfall_on_the_fused_kernels(engine, fmt, n, width):
         assert np.array_equal(gpu[k], plain[k]), k
 
 
+@pytest.mark.parametrize("fmt,n,width,wf", [("CS16", 64, 2100, False), ("CU8", 128, 1100, False), ("CS16", 256, 520, True), ("CF32", 512, 270, False),
+                                            ("CS16", 512, 136, False), ("CU8", 1024, 140, False), ("CS8", 1024, 72, True)])
+def test_split_real_on_the_warp_kernel(engine, fmt, n, width, wf):
+    """channelMode inside render_w_kernel (N = 64 .. 1024, the reference's everyday sizes): bin i pairs with bin n - i in lane
+    (T - t) mod T of the same frame, exchanged through the frame's area of the warp's buffer; full and partial tiles, both layouts."""
+    S = n * (width // 2 + 3) + 17
+    buf = O.synth(fmt, 0, S, S, 0x5EC7F000 + n + width).tobytes()
+    gpu, ora, nbad = run_both(engine, buf, fmt, n, width, "hann", channel_mode=True, waterfall=wf, want_db=False)
+    plan = engine.kernel_plan(fmt, n, True)
+    assert "render_w_kernel" in plan and "split-real" in plan
+    g = gray_from_image(gpu["image"], CM256, n, width, wf)
+    assert (g[:, n // 2] == 0).all() and gpu["dBfs_min"] == -np.inf
+
+
 @pytest.mark.parametrize("fmt,width,wf", [("CS16", 40, False), ("CF32", 21, False), ("CS16", 24, True), ("CU8", 64, False)])
 def test_split_real_on_the_fused_kernel(engine, fmt, width, wf):
     """channelMode (two real channels, lib/fft_nayuki.js:103-119) inside render_r64_kernel: bin i pairs with bin n - i held by

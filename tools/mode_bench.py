@@ -8,7 +8,7 @@ from spectro_b200 import windows, cmaps
 dev=torch.device("cuda",0); eng=spectro_b200.Engine(0)
 st=torch.cuda.Stream(device=dev); torch.cuda.set_stream(st); eng.set_stream(st.cuda_stream)
 cm=cmaps.cmap_bytes([list(c) for c in cmaps.cmaps["viridis_cmap"]])
-for fmt,n,S,wf,chm in (("CS16",4096,1<<26,False,False),("CS16",4096,1<<26,True,False),("CS16",4096,1<<26,False,True),("CU8",1024,1<<26,True,False),("CU8",1024,1<<26,False,False)):
+for fmt,n,S,wf,chm in (("CS16",4096,1<<26,False,False),("CS16",4096,1<<26,True,False),("CS16",4096,1<<26,False,True),("CU8",1024,1<<26,True,False),("CU8",1024,1<<26,False,False),("CU8",1024,1<<26,False,True),("CS16",512,1<<26,False,True),("CS16",128,1<<26,False,True)):
     sw=4 if fmt=="CS16" else 2; width=S//n
     d_in=torch.empty(S*sw+256,dtype=torch.uint8,device=dev); eng.synth_fill(d_in.data_ptr(),fmt,0,S,S,5)
     d_img=torch.empty(4*width*n,dtype=torch.uint8,device=dev); d_g=torch.empty(3*width,dtype=torch.uint8,device=dev)
