@@ -28,7 +28,12 @@ cases = [("CS16", 4096, 32, False, False),      # render_r64_kernel, full tiles
          ("CF32", 1024, 56, False, False),      # render_w_kernel 32 x 32
          ("CU12", 64, 520, False, False),       # render_w_kernel 8 x 8
          ("CF32", 8192, 40, False, False),      # four-step, L2-ring form (render_big_kernel; SP_FOURSTEP=ring below)
-         ("CS16", 65536, 24, False, False)]     # ring form, R = 16
+         ("CS16", 65536, 24, False, False),     # ring form, R = 16
+         # round 2, second half
+         ("CU8", 1024, 72, True, False),        # render_w_kernel 32 x 32, waterfall rows from its store warps (case 10 ran on rc in round 1)
+         ("CS16", 128, 296, True, True),        # render_w_kernel 16 x 8, split-real + waterfall, partial tile
+         ("CF32", 512, 136, False, True),       # render_w_kernel 32 x 16, split-real
+         ("CS8", 2048, 40, True, False)]        # render_rc_kernel N = 2048 with the interleaved exchange stores, waterfall
 os.environ.setdefault("SP_FOURSTEP", "ring")   # cases 7, 8 predate the ring kernel and ask for it too now; the HBM form keeps its round-1 record
 only = [int(a) for a in sys.argv[1:]]
 for i, (fmt, n, width, wf, chm) in enumerate(cases):
