@@ -186,6 +186,17 @@ int sp_render(sp_engine *e, const sp_request *rq, sp_reply *rp);
 int sp_render_enqueue(sp_engine *e, const sp_request *rq, sp_reply *rp);
 int sp_render_finish(sp_engine *e, sp_reply *rp);
 
+/* Asynchronous form of sp_render() for host buffers on a single-device engine: the message is enqueued (chunked copies in,
+ * kernels, copies out on the engine's streams) and the call returns a ticket; sp_render_wait() blocks until that message's
+ * reply is complete and fills dBfs_min / dBfs_max.  Up to TWO messages may be in flight: the copy-out tail of one overlaps
+ * the copy-in head of the next (a third call first collects the oldest).  Replaces the reference's posting of messages to
+ * several workers and collecting the replies as they arrive (lib/spectroplot.js:1206-1238, worker.onmessage).  `rp` and
+ * every buffer `rq` / `rp` point to must stay alive and untouched until the ticket has been waited for; page-locked host
+ * memory (sp_host_alloc_pinned) is needed for the copies to overlap.  Short messages and device-resident ones are simply
+ * rendered before the call returns.  Results are bit-identical to sp_render(). */
+int sp_render_async(sp_engine *e, const sp_request *rq, sp_reply *rp, int *ticket);
+int sp_render_wait(sp_engine *e, int ticket);
+
 /* Device-resident shards of ONE message on a multi-device engine: rq[g] / rp[g] (g = 0 .. ndev-1) describe the
  * frame-range shard that lives on device g - bytes, image band, gauges, both histograms and minmax_dev are device
  * pointers on THAT device (SP_F_BUFFER_ON_DEVICE | SP_F_REPLY_ON_DEVICE, shard fields set; allocate with

@@ -186,6 +186,20 @@ struct sp_engine {
     std::vector<float> h_window, h_window_t; // last uploaded window / LUT (upload only on change)
     std::vector<uint32_t> h_lut;
     double *stats_src = nullptr;
+    // sp_render_async: up to two host-buffer messages in flight (the copy-out tail of one overlaps the copy-in head of the next)
+    struct Inflight {
+        cudaEvent_t done = nullptr, reply = nullptr;
+        uint8_t *bounce = nullptr;           // pinned: [16 stats][W mins][W maxs][W amps][8 * 1000 cB][8 * cmap_len c]
+        size_t bounce_cap = 0;
+        sp_reply *rp = nullptr;
+        long long width = 0;
+        int cmap_len = 0, launches = 0, ticket = -1;
+        bool busy = false;
+    } inflight[2];
+    int next_ticket = 0;
+    cudaStream_t s_done = nullptr;
+    bool pipe_used[2] = { false, false };    // pin[b] / pimg[b] have been used by an earlier chunk (of this or of the previous message)
+    bool ev_out_valid[2] = { false, false }; // ev_out[b] has been recorded
     bool pending = false;
     long long pend_width = 0;
     int pend_cmap_len = 0;
@@ -329,6 +343,12 @@ extern "C" void sp_destroy(sp_engine *e)
         if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
     }
     if (e->ev_setup) cudaEventDestroy(e->ev_setup);
+    for (auto &s : e->inflight) {
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.reply) cudaEventDestroy(s.reply);
+        if (s.bounce) cudaFreeHost(s.bounce);
+    }
+    if (e->s_done) cudaStreamDestroy(e->s_done);
     if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
     if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -1164,7 +1184,8 @@ static long long pipeline_chunk_frames(const sp_request *rq)
     return (rq->width >= 3 * ch) ? ch : 0;       // short messages: single shot
 }
 
-static int render_pipelined(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, long long ch, const Placement *pl)
+static int render_pipelined(sp_engine *e, const sp_request *rq, sp_reply *rp, Job &j, long long ch, const Placement *pl,
+                            sp_engine::Inflight *slot = nullptr)
 {
     const int n = rq->n, sw = sp::sample_width(rq->format);
     const long long W = rq->width;
@@ -1209,13 +1230,14 @@ static int render_pipelined(sp_engine *e, const sp_request *rq, sp_reply *rp, Jo
         if (b1 > rq->byte_length || msg_last) b1 = rq->byte_length;
         if (b0 > b1) b0 = b1;
         if (b1 - b0 + 16 > in_cap) return fail(e, SP_E_RANGE, "internal: pipeline chunk larger than its buffer");
-        // input buffer b is free once the render of chunk c-2 is done
-        if (c >= 2) CU(cudaStreamWaitEvent(e->s_h2d, e->ev_comp[b], 0));
+        // input buffer b is free once the render of its previous user is done (chunk c-2, or a chunk of the previous message:
+        // sp_render_async keeps two messages in flight)
+        if (c >= 2 || e->pipe_used[b]) CU(cudaStreamWaitEvent(e->s_h2d, e->ev_comp[b], 0));
         CU(cudaMemcpyAsync(e->pin[b].p, (const uint8_t *)rq->buffer + b0, b1 - b0, cudaMemcpyHostToDevice, e->s_h2d));
         CU(cudaEventRecord(e->ev_in[b], e->s_h2d));
         // render: needs the input, and image tile b drained by the D2H of chunk c-2
         CU(cudaStreamWaitEvent(e->stream, e->ev_in[b], 0));
-        if (c >= 2) CU(cudaStreamWaitEvent(e->stream, e->ev_out[b], 0));
+        if ((c >= 2 || e->pipe_used[b]) && e->ev_out_valid[b]) CU(cudaStreamWaitEvent(e->stream, e->ev_out[b], 0));
         Params q = j.p;
         q.buf = (const uint8_t *)e->pin[b].p;
         q.valid_bytes = b1 - b0;
@@ -1237,9 +1259,30 @@ static int render_pipelined(sp_engine *e, const sp_request *rq, sp_reply *rp, Jo
                 CU(cudaMemcpy2DAsync(rp->image + 4 * (x0 + (pl ? pl->col0 : 0)), (size_t)4 * (pl ? pl->pitch_frames : W), e->pimg[b].p,
                                      (size_t)4 * cw, (size_t)4 * cw, (size_t)n, cudaMemcpyDeviceToHost, e->s_d2h));
             CU(cudaEventRecord(e->ev_out[b], e->s_d2h));
+            e->ev_out_valid[b] = true;
         }
+        e->pipe_used[b] = true;
     }
     if ((rc = enqueue_end(e, j))) return rc;
+    if (slot) {
+        // asynchronous form: the small reply arrays go through the slot's pinned bounce buffer (the caller's arrays may be pageable,
+        // which would make the copies synchronous); the message is complete when they and the last image tiles have arrived
+        uint8_t *b = slot->bounce;
+        CU(cudaMemcpyAsync(b, e->stats_src ? (void *)e->stats_src : e->stats.p, 16, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(b + 16, j.d_gmin, (size_t)W, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(b + 16 + W, j.d_gmax, (size_t)W, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(b + 16 + 2 * W, j.d_gamp, (size_t)W, cudaMemcpyDeviceToHost, e->stream));
+        uint8_t *hb = b + 16 + ((3 * W + 15) / 16) * 16;
+        CU(cudaMemcpyAsync(hb, j.d_cb, 8 * SP_CB_HIST_SIZE, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(hb + 8 * SP_CB_HIST_SIZE, j.d_c, 8 * (size_t)rq->cmap_len, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaEventRecord(slot->reply, e->stream));
+        CU(cudaStreamWaitEvent(e->s_done, slot->reply, 0));
+        for (int i = 0; i < 2; i++)
+            if (j.d_image && e->ev_out_valid[i]) CU(cudaStreamWaitEvent(e->s_done, e->ev_out[i], 0));
+        CU(cudaEventRecord(slot->done, e->s_done));
+        slot->launches = e->launches;
+        return SP_OK;
+    }
     if (rp->gauge_mins) CU(cudaMemcpyAsync(rp->gauge_mins, j.d_gmin, (size_t)W, cudaMemcpyDeviceToHost, e->stream));
     if (rp->gauge_maxs) CU(cudaMemcpyAsync(rp->gauge_maxs, j.d_gmax, (size_t)W, cudaMemcpyDeviceToHost, e->stream));
     if (rp->gauge_amps) CU(cudaMemcpyAsync(rp->gauge_amps, j.d_gamp, (size_t)W, cudaMemcpyDeviceToHost, e->stream));
@@ -1464,6 +1507,79 @@ extern "C" int sp_render(sp_engine *e, const sp_request *rq, sp_reply *rp)
     if (!e || !rq || !rp) return fail(e, SP_E_INVAL, "null argument");
     if (!e->subs.empty()) return render_multi(e, rq, rp);
     return render_one(e, rq, rp, nullptr);
+}
+
+// ---- asynchronous host-buffer messages (the reference posts messages to several workers and collects the replies as they come,
+// lib/spectroplot.js:1206-1238; here two messages may be in flight on ONE engine so that the copy-out tail of a message
+// overlaps the copy-in head of the next).  The reply struct and every buffer it points to must stay alive until sp_render_wait.
+static int wait_slot(sp_engine *e, sp_engine::Inflight &s)
+{
+    if (!s.busy) return SP_OK;
+    CU(cudaEventSynchronize(s.done));
+    sp_reply *rp = s.rp;
+    const size_t W = (size_t)s.width;
+    const uint8_t *b = s.bounce;
+    double st[2];
+    memcpy(st, b, 16);
+    rp->dBfs_min = st[0];
+    rp->dBfs_max = st[1];
+    if (rp->gauge_mins) memcpy(rp->gauge_mins, b + 16, W);
+    if (rp->gauge_maxs) memcpy(rp->gauge_maxs, b + 16 + W, W);
+    if (rp->gauge_amps) memcpy(rp->gauge_amps, b + 16 + 2 * W, W);
+    const uint8_t *hb = b + 16 + ((3 * W + 15) / 16) * 16;
+    if (rp->cB_hist) memcpy(rp->cB_hist, hb, 8 * SP_CB_HIST_SIZE);
+    if (rp->c_hist) memcpy(rp->c_hist, hb + 8 * SP_CB_HIST_SIZE, 8 * (size_t)s.cmap_len);
+    rp->device_ms = 0.0;                      // (per-message device time is not tracked for overlapping messages)
+    rp->kernel_launches = s.launches;
+    s.busy = false;
+    return SP_OK;
+}
+
+extern "C" int sp_render_async(sp_engine *e, const sp_request *rq, sp_reply *rp, int *ticket)
+{
+    if (!e || !rq || !rp || !ticket) return fail(e, SP_E_INVAL, "null argument");
+    if (!e->subs.empty()) return fail(e, SP_E_INVAL, "sp_render_async works on a single-device engine");
+    CU(cudaSetDevice(e->dev));
+    sp_engine::Inflight &s = e->inflight[e->next_ticket & 1];
+    int rc = wait_slot(e, s);                              // at most two messages in flight: the older one is collected first
+    if (rc) return rc;
+    *ticket = e->next_ticket;
+    s.ticket = e->next_ticket++;
+    const bool host_io = !(rq->flags & (SP_F_BUFFER_ON_DEVICE | SP_F_REPLY_ON_DEVICE));
+    const long long ch = (host_io && rq->width > 0 && rq->n > 0 && rq->byte_length > 0) ? pipeline_chunk_frames(rq) : 0;
+    if (ch <= 0) return render_one(e, rq, rp, nullptr);    // short or device-resident message: nothing to overlap, done on return
+    if (!s.done) {
+        CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s.reply, cudaEventDisableTiming));
+    }
+    if (!e->s_done) CU(cudaStreamCreateWithFlags(&e->s_done, cudaStreamNonBlocking));
+    const size_t need = 16 + (((size_t)3 * (size_t)rq->width + 15) / 16) * 16 + 8 * (size_t)(SP_CB_HIST_SIZE + SP_MAX_CMAP);
+    if (s.bounce_cap < need) {
+        if (s.bounce) cudaFreeHost(s.bounce);
+        s.bounce = nullptr; s.bounce_cap = 0;
+        CU(cudaHostAlloc((void **)&s.bounce, need, cudaHostAllocDefault));
+        s.bounce_cap = need;
+    }
+    Job j;
+    j.pipelined = true;
+    if ((rc = prepare(e, rq, rp, j, false, nullptr))) return rc;
+    if ((rc = render_pipelined(e, rq, rp, j, ch, nullptr, &s))) return rc;
+    s.rp = rp;
+    s.width = rq->width;
+    s.cmap_len = rq->cmap_len;
+    s.busy = true;
+    return SP_OK;
+}
+
+extern "C" int sp_render_wait(sp_engine *e, int ticket)
+{
+    if (!e) return SP_E_INVAL;
+    if (!e->subs.empty()) return fail(e, SP_E_INVAL, "sp_render_async works on a single-device engine");
+    if (ticket < 0 || ticket >= e->next_ticket) return fail(e, SP_E_INVAL, "unknown ticket %d", ticket);
+    sp_engine::Inflight &s = e->inflight[ticket & 1];
+    if (s.ticket != ticket) return SP_OK;                  // already collected (by a later sp_render_async that needed the slot)
+    CU(cudaSetDevice(e->dev));
+    return wait_slot(e, s);
 }
 
 extern "C" int sp_render_zooms(sp_engine *e, const sp_request *rq, int nlevels, const int64_t *widths, sp_reply *replies)

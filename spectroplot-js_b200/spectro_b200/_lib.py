@@ -34,7 +34,7 @@ SYMBOLS = ["sp_abi_version", "sp_format_from_name", "sp_format_name", "sp_sample
            "sp_render_finish", "sp_render_zooms", "sp_decode", "sp_render_db", "sp_device_alloc", "sp_device_free", "sp_memcpy_h2d",
            "sp_memcpy_d2h", "sp_host_alloc_pinned", "sp_host_free_pinned", "sp_device_sync", "sp_synth_fill",
            "sp_synth_lut", "sp_device_count", "sp_sm_count", "sp_kernel_plan", "sp_profile_enable", "sp_profile_read",
-           "sp_render_shards", "sp_select_device", "sp_build_id", "sp_profile_sample"]
+           "sp_render_shards", "sp_select_device", "sp_build_id", "sp_profile_sample", "sp_render_async", "sp_render_wait"]
 
 
 class SpError(RuntimeError):
@@ -86,6 +86,8 @@ def load():
     for fn in ("sp_render", "sp_render_enqueue"):
         getattr(lib, fn).argtypes = [C.c_void_p, C.POINTER(Request), C.POINTER(Reply)]
     lib.sp_render_finish.argtypes = [C.c_void_p, C.POINTER(Reply)]
+    lib.sp_render_async.argtypes = [C.c_void_p, C.POINTER(Request), C.POINTER(Reply), C.POINTER(C.c_int)]
+    lib.sp_render_wait.argtypes = [C.c_void_p, C.c_int]
     lib.sp_render_shards.argtypes = [C.c_void_p, C.POINTER(Request), C.POINTER(Reply)]
     lib.sp_select_device.argtypes = [C.c_void_p, C.c_int]
     lib.sp_render_db.argtypes = [C.c_void_p, C.POINTER(Request), C.c_void_p]
@@ -315,6 +317,30 @@ class Engine:
         return dict(image=img, gauge_mins=gmin, gauge_maxs=gmax, gauge_amps=gamp, cB_hist=cb, c_hist=ch,
                     dBfs_min=rp.dBfs_min, dBfs_max=rp.dBfs_max, device_ms=rp.device_ms,
                     kernel_launches=rp.kernel_launches)
+
+    def render_async(self, buf, fmt, n, width, windowc, block_norm, gain, range_, cmap, channel_mode=False,
+                     waterfall=False, shard=None, byte_length=None, out_image: np.ndarray | None = None):
+        """sp_render_async: enqueue a host-buffer message and return a handle for `wait`; up to two may be in flight."""
+        rq, keep = self.make_request(buf, fmt, n, width, windowc, block_norm, gain, range_, cmap, channel_mode,
+                                     waterfall, 0, byte_length, shard)
+        width, n = int(width), int(n)
+        img = out_image if out_image is not None else np.empty(4 * width * n, np.uint8)
+        gmin = np.empty(width, np.uint8); gmax = np.empty(width, np.uint8); gamp = np.empty(width, np.uint8)
+        cb = np.zeros(CB_HIST_SIZE, np.uint64); ch = np.zeros(rq.cmap_len, np.uint64)
+        rp = Reply(_vp(img), _vp(gmin), _vp(gmax), _vp(gamp), _vp(cb), _vp(ch), 0.0, 0.0, 0.0, 0, None)
+        ticket = C.c_int(-1)
+        self._check(self.lib.sp_render_async(self.h, C.byref(rq), C.byref(rp), C.byref(ticket)))
+        return dict(ticket=ticket.value, rq=rq, rp=rp, keep=keep, img=img, gmin=gmin, gmax=gmax, gamp=gamp, cb=cb, ch=ch,
+                    shape=(width, n, 4) if waterfall else (n, width, 4))
+
+    def wait(self, handle) -> dict:
+        """sp_render_wait: block until the message of `handle` is complete; returns the reply dict of `render`."""
+        self._check(self.lib.sp_render_wait(self.h, int(handle["ticket"])))
+        rp, shape = handle["rp"], handle["shape"]
+        img = handle["img"][: shape[0] * shape[1] * 4].reshape(shape)
+        return dict(image=img, gauge_mins=handle["gmin"], gauge_maxs=handle["gmax"], gauge_amps=handle["gamp"],
+                    cB_hist=handle["cb"], c_hist=handle["ch"], dBfs_min=rp.dBfs_min, dBfs_max=rp.dBfs_max,
+                    device_ms=rp.device_ms, kernel_launches=rp.kernel_launches)
 
     def render_zooms(self, buf, fmt, n, widths, windowc, block_norm, gain, range_, cmap, channel_mode=False,
                      waterfall=False):

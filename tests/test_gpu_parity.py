@@ -636,6 +636,40 @@ def test_randomized_option_sweep(engine, case):
              label="random case %d" % i)
 
 
+def test_async_messages_equal_synchronous_renders(engine):
+    """sp_render_async / sp_render_wait: messages in flight two at a time through the pipelined host path (the device chunk
+    buffers, the accumulators and the gauges are shared by consecutive messages) must reproduce sp_render byte for byte, whatever
+    the order of waits; different windows / colormaps / sizes in a row exercise the table re-uploads between overlapping messages."""
+    import spectro_b200
+    msgs = [("CS16", 4096, 1000, "hann", CM256, False), ("CS16", 4096, 1000, "hann", CM256, False), ("CU8", 1024, 2400, "blackmanHarris", injective_cmap(64), False),
+            ("CS16", 4096, 520, "bartlett", CM256, True), ("CF32", 512, 3000, "hann", CM256, False), ("CS16", 4096, 1000, "hann", CM256, False)]
+    bufs, sync = [], []
+    for i, (fmt, n, width, win, cm, wf) in enumerate(msgs):
+        S = n * (width // 2 + 3) + 29
+        pb = spectro_b200.PinnedBuffer(S * O.SAMPLE_WIDTH[O.fmt_id(fmt)])
+        pb.array[:] = np.frombuffer(O.synth(fmt, 0, S, S, 0xA5A50000 + i).tobytes(), np.uint8)
+        bufs.append(pb)
+        w, wt = O.window(win, n)
+        sync.append(engine.render(pb.array, fmt, n, width, w, 1 / wt, 6, 30, cm, waterfall=wf))
+        assert sync[-1]["kernel_launches"] > 0
+    outs = [spectro_b200.PinnedBuffer(4 * m[1] * m[2]) for m in msgs]
+    handles = []
+    for i, (fmt, n, width, win, cm, wf) in enumerate(msgs):
+        w, wt = O.window(win, n)
+        handles.append(engine.render_async(bufs[i].array, fmt, n, width, w, 1 / wt, 6, 30, cm, waterfall=wf, out_image=outs[i].array))
+    for i in (1, 0, 2, 5, 4, 3):                               # any order, also after the slot was recycled
+        r = engine.wait(handles[i])
+        for k in ("image", "cB_hist", "c_hist", "gauge_mins", "gauge_maxs", "gauge_amps"):
+            assert np.array_equal(r[k], sync[i][k]), (i, k)
+        assert r["dBfs_min"] == sync[i]["dBfs_min"] and r["dBfs_max"] == sync[i]["dBfs_max"], i
+    # a synchronous render between asynchronous ones
+    h = engine.render_async(bufs[0].array, *msgs[0][:3], *(lambda w: (w[0], 1 / w[1]))(O.window("hann", 4096)), 6, 30, CM256, out_image=outs[0].array)
+    w, wt = O.window("hann", 4096)
+    mid = engine.render(bufs[1].array, "CS16", 4096, 1000, w, 1 / wt, 6, 30, CM256)
+    r = engine.wait(h)
+    assert np.array_equal(mid["image"], sync[1]["image"]) and np.array_equal(r["image"], sync[0]["image"])
+
+
 # ------------------------------------------------------------------ multi-device engine (sp_create with ndev > 1)
 def _gpu_count():
     try:
