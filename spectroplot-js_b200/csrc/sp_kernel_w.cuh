@@ -67,6 +67,28 @@ template <int LOG2P, int LOG2T, int FMT> struct WCfg {
                                        + 128 + 1024 /* LUT alignment */;
 };
 
+// min / max over the T lanes of a frame (aligned groups of T lanes).  A __reduce_*_sync with a partial mask makes the warp's
+// FW groups run the collective one after the other (ncu: 10 % of the stall samples of the N = 128 kernel sat there as
+// branch_resolving); an xor butterfly over log2 T steps keeps all 32 lanes together.
+template <int T> __device__ __forceinline__ unsigned group_min(unsigned v)
+{
+    if constexpr (T == 32) return __reduce_min_sync(0xffffffffu, v);
+    else {
+#pragma unroll
+        for (int o = 1; o < T; o <<= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+}
+template <int T> __device__ __forceinline__ unsigned group_max(unsigned v)
+{
+    if constexpr (T == 32) return __reduce_max_sync(0xffffffffu, v);
+    else {
+#pragma unroll
+        for (int o = 1; o < T; o <<= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+}
+
 // twW: [P][T] float2 = W_N^{t*k} (k = 0 .. P-1; double -> fp32 once)
 // OPT = true: the same kernel with the split-real post-process (lib/fft_nayuki.js:103-119) compiled in; the launcher takes it
 // for channelMode messages only, so the plain kernel carries neither its registers nor its code.
@@ -228,8 +250,6 @@ __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_
     // ================= FFT warps: every warp walks its own warp-steps of FW frames =================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(B::FFT_REGS));
     unsigned fpar = 0;                      // parity of this warp's step counter (mbarrier phase, s_off slot)
-    constexpr unsigned GROUP_BASE_MASK = T == 32 ? 0xffffffffu : ((1u << (T & 31)) - 1u);
-    const unsigned gmask = GROUP_BASE_MASK << (f * T);                           // lanes of this frame
     // thread-invariant tables: window coefficient of sample t + T a; twiddle W_N^{t k0}
     float win[P];
 #pragma unroll
@@ -372,11 +392,11 @@ __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_
                 }
             unsigned umn, umx;
             if constexpr (FLOAT_IN) {
-                umn = __reduce_min_sync(gmask, umin_i);
-                umx = __reduce_max_sync(gmask, umax_i);
+                umn = group_min<T>(umin_i);
+                umx = group_max<T>(umax_i);
             } else {
-                umn = __reduce_min_sync(gmask, __float_as_uint(amin));
-                umx = __reduce_max_sync(gmask, __float_as_uint(amax));
+                umn = group_min<T>(__float_as_uint(amin));
+                umx = group_max<T>(__float_as_uint(amax));
             }
             if (__any_sync(0xffffffffu, umn < 0x00800000u || umx >= 0x7f800000u)) {
                 // rare (warp-uniform): a frame of this warp holds |X|^2 == 0 (flushed), +inf or NaN: see render_r64_kernel
@@ -396,8 +416,8 @@ __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_
                 nzero = __reduce_add_sync(0xffffffffu, nzero);
                 nbad = __reduce_add_sync(0xffffffffu, nbad);
                 nnan = __reduce_add_sync(0xffffffffu, nnan);
-                umn = __reduce_min_sync(gmask, __float_as_uint(mn));
-                umx = __reduce_max_sync(gmask, __float_as_uint(mx));
+                umn = group_min<T>(__float_as_uint(mn));
+                umx = group_max<T>(__float_as_uint(mx));
                 if (lane == 0) {
                     if (nzero) atomicAdd(&s_jh[JH_ZERO], nzero);
                     if (nbad) atomicAdd(&s_jh[JH_BAD], nbad);
