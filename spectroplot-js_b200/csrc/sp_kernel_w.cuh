@@ -127,14 +127,29 @@ __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_
     const unsigned jh_base = smem_u32(s_jh) - (JH_MAGIC_BITS << 2);
     const int nfull = p.n_full;
 
-    // lane 0 of a warp: start the bulk copies of the FW frames xr .. xr + FW - 1 (chunk relative) into the warp's buffer
+    // a warp: start the bulk copies of the FW frames xr .. xr + FW - 1 (chunk relative) into the warp's buffer (issued by lane 0)
     auto stage = [&](long long xr, unsigned par) {
+        // called by the whole warp.  FW = 4 (N = 64, 128): lane i works out the position of frame i (double arithmetic,
+        // lib/worker.js:72) and lane 0 collects them - four positions in the time of one while the warp would otherwise wait for a
+        // serial loop in lane 0 (+4 % at N = 128, +3 % at N = 64; with one or two frames per warp the warp-wide double
+        // instructions cost more than they save: -2 .. -4 %, so those keep the loop in lane 0)
         long long p0[FW];
-#pragma unroll
-        for (int i = 0; i < FW; i++) {
+        if constexpr (FW >= 4) {
+            const int i = lane < FW ? lane : FW - 1;
             const long long xc = xr + i < p.chunk_frames ? xr + i : p.chunk_frames - 1;   // partial last tile: redo the last frame
             const long long xgl = p.frame_first + p.chunk_first + xc;
-            p0[i] = (long long)__dadd_rn(0.5, __dmul_rn(p.stride, (double)xgl)) - p.sample_base;   // lib/worker.js:72
+            const long long mine = (long long)__dadd_rn(0.5, __dmul_rn(p.stride, (double)xgl)) - p.sample_base;   // lib/worker.js:72
+#pragma unroll
+            for (int k = 0; k < FW; k++) p0[k] = __shfl_sync(0xffffffffu, mine, k);
+            if (lane != 0) return;
+        } else {
+            if (lane != 0) return;
+#pragma unroll
+            for (int i = 0; i < FW; i++) {
+                const long long xc = xr + i < p.chunk_frames ? xr + i : p.chunk_frames - 1;
+                const long long xgl = p.frame_first + p.chunk_first + xc;
+                p0[i] = (long long)__dadd_rn(0.5, __dmul_rn(p.stride, (double)xgl)) - p.sample_base;
+            }
         }
         int *off = s_off + (warp * 2 + par) * FW;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -261,7 +276,7 @@ __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_
     }
     // frames of warp-step (h, j) of a tile: h*HF + (j*NW + warp)*FW .. + FW - 1
     auto step_first = [&](long long tl, int h, int j) -> long long { return tl * F + h * HF + (j * NW + warp) * FW; };
-    if (lane == 0 && tile < p.ntiles) stage(step_first(tile, 0, 0), 0);
+    if (tile < p.ntiles) stage(step_first(tile, 0, 0), 0);
 
     while (tile < p.ntiles) {
         const long long next_tile = tile + gridDim.x;
@@ -322,7 +337,7 @@ __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_
                 if (hj + 1 < 2 * B::WSH) stage(step_first(tile, (hj + 1) / B::WSH, (hj + 1) % B::WSH), fpar);
                 else if (next_tile < p.ntiles) stage(step_first(next_tile, 0, 0), fpar);
             };
-            if (lane == 0 && !split) prefetch();
+            if (!split) prefetch();
             if (j == 0) mbar_wait(s_empty + h, (kk + 1) & 1);           // the store warps are done with this staging half (previous tile)
 #pragma unroll
             for (int q = 0; q < Q; q++) {
@@ -357,7 +372,7 @@ __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_
                         v[r] = nv;
                     }
                     __syncwarp();                                       // now the buffer is free
-                    if (lane == 0) prefetch();
+                    prefetch();
                 }
             }
 
