@@ -34,6 +34,12 @@
 #ifndef SP_W_TWREG32
 #define SP_W_TWREG32 1
 #endif
+#ifndef SP_W_SEP
+#define SP_W_SEP 1
+#endif
+#ifndef SP_W_STSB
+#define SP_W_STSB 1         // exchange stores between the twiddle products (0: in a row after them; the same within noise at N = 512)
+#endif
 
 namespace sp {
 
@@ -58,7 +64,16 @@ template <int LOG2P, int LOG2T, int FMT> struct WCfg {
     // (a multiple of 16 bytes: bulk-copy destination)
     static constexpr int RAWP = N * SWB + ((T * SWB >= 128 || T * SWB < 16 || (T * SWB) % 16 != 0) ? 32 : (T * SWB >= 32 ? T * SWB : T * SWB + 128));
     static_assert(RAWP % 16 == 0, "raw slots are bulk-copy destinations");
+#if SP_W_SEP
+    // the raw frames and the exchange area of a warp do not share bytes: the exchange stores need no "raw frame consumed" fence (they
+    // ride between the twiddle products) and the next frames' bulk copy starts as soon as the warp has decoded, not after pass B
+    static constexpr int RAW_BYTES = (FW * RAWP + 15) & ~15;
+    static constexpr int XBYTES = RAW_BYTES + ((FW * FSTR * 8 + 15) & ~15);
+    static constexpr bool STS_BETWEEN = SP_W_STSB != 0;
+#else
+    static constexpr int RAW_BYTES = 0;
     static constexpr int XBYTES = ((FW * FSTR * 8 > FW * RAWP ? FW * FSTR * 8 : FW * RAWP) + 15) & ~15;
+#endif
     static constexpr int FPITCH = (HF + 31) / 32 * 32 + FW;                      // staging words per word column: STS.32 of a warp conflict-free
     static constexpr int HALF_WORDS = (N / 4) * FPITCH;
     static constexpr bool TW_SMEM = P > 16 && !SP_W_TWREG32;                     // twiddles from shared memory (31 per thread do not fit 152 registers)
@@ -115,7 +130,7 @@ __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_
     const int warp = tid >> 5, lane = tid & 31;
     const int f = lane / T, t = lane % T;   // frame of the warp-step, column
     unsigned char *xs = s_x + (size_t)(warp < NW ? warp : 0) * B::XBYTES;
-    float2 *X = reinterpret_cast<float2 *>(xs) + f * B::FSTR;                    // this frame's exchange area
+    float2 *X = reinterpret_cast<float2 *>(xs + B::RAW_BYTES) + f * B::FSTR;     // this frame's exchange area
     uint64_t *mbar = s_mbar + (warp < NW ? warp : 0);
 
     for (int i = tid; i < JH_SIZE; i += B::THREADS) s_jh[i] = 0;
@@ -313,14 +328,40 @@ __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_
                     if (i > 0) v[2 * i] = cmul(v[2 * i], make_float2(w4.x, w4.y));
                     v[2 * i + 1] = cmul(v[2 * i + 1], make_float2(w4.z, w4.w));
                 }
+#if SP_W_SEP
+#pragma unroll
+                for (int k = 0; k < P; k++) cst(X + k * B::XP + t, v[k]);
+#endif
             } else {
+#if SP_W_SEP
+                if constexpr (B::STS_BETWEEN) {
+                    cst(X + t, v[0]);
+#pragma unroll
+                    for (int k = 1; k < P; k++) { v[k] = cmul(v[k], tw[k]); cst(X + k * B::XP + t, v[k]); }   // Z[k0][t], between the products
+                } else {
+#pragma unroll
+                    for (int k = 1; k < P; k++) v[k] = cmul(v[k], tw[k]);
+#pragma unroll
+                    for (int k = 0; k < P; k++) cst(X + k * B::XP + t, v[k]);
+                }
+#else
 #pragma unroll
                 for (int k = 1; k < P; k++) v[k] = cmul(v[k], tw[k]);
+#endif
             }
+#if !SP_W_SEP
             __syncwarp();                                               // every lane has consumed its raw frame
 #pragma unroll
             for (int k = 0; k < P; k++) cst(X + k * B::XP + t, v[k]);   // Z[k0][t]
-            __syncwarp();
+#endif
+            __syncwarp();                                               // the rows are complete (and every lane has decoded its raw frame)
+            auto prefetch = [&]() {
+                if (hj + 1 < 2 * B::WSH) stage(step_first(tile, (hj + 1) / B::WSH, (hj + 1) % B::WSH), fpar);
+                else if (next_tile < p.ntiles) stage(step_first(next_tile, 0, 0), fpar);
+            };
+#if SP_W_SEP
+            prefetch();                                                 // the raw area is free: start the bulk copy of the warp's next frames
+#endif
             // ---------------- pass B: thread u = t owns rows k0 = u + T*q: Q transforms of length T ----------------
 #pragma unroll
             for (int q = 0; q < Q; q++) {
@@ -331,13 +372,11 @@ __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_
                     v[q * T + 2 * i] = cpk(z.x, z.y); v[q * T + 2 * i + 1] = cpk(z.z, z.w);
                 }
             }
-            __syncwarp();                                               // the exchange buffer is free: prefetch the warp's next frames
-            const bool split = OPT && p.channel_mode;                   // split-real needs the buffer once more, see below
-            auto prefetch = [&]() {
-                if (hj + 1 < 2 * B::WSH) stage(step_first(tile, (hj + 1) / B::WSH, (hj + 1) % B::WSH), fpar);
-                else if (next_tile < p.ntiles) stage(step_first(next_tile, 0, 0), fpar);
-            };
-            if (!split) prefetch();
+            __syncwarp();                                               // the exchange area is free (next step's stores, split-real below)
+            const bool split = OPT && p.channel_mode;
+#if !SP_W_SEP
+            if (!split) prefetch();                                     // shared bytes: split-real needs the buffer once more, see below
+#endif
             if (j == 0) mbar_wait(s_empty + h, (kk + 1) & 1);           // the store warps are done with this staging half (previous tile)
 #pragma unroll
             for (int q = 0; q < Q; q++) {
@@ -372,7 +411,9 @@ __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_
                         v[r] = nv;
                     }
                     __syncwarp();                                       // now the buffer is free
+#if !SP_W_SEP
                     prefetch();
+#endif
                 }
             }
 
