@@ -297,9 +297,23 @@ def random_cases(W, count=40, seed=20261017):
         made += 1
 
 
+def round2_option_cases(W):
+    """channelMode / turnFlip at the reference's menu sizes (lib/example.html:23-84), at widths that put whole groups of 8 frames on
+    render_w_kernel (added when it took over both options from the generic kernel)."""
+    cm256 = injective_cmap(256)
+    run_case(W, "r2_cs16_n1024_hann_w17_split", "CS16", 1024, 17, "hann", cm256, 6, 30, synth("CS16", 1024 * 9 + 77, 0x5EC70201), channel_mode=True)
+    run_case(W, "r2_cu8_n512_bh_viridis_w24_split_wf", "CU8", 512, 24, "blackmanHarris", "viridis", 6, 30, synth("CU8", 512 * 13 + 5, 0x5EC70202), channel_mode=True, waterfall=True)
+    run_case(W, "r2_cf32_n256_hann_w40_split", "CF32", 256, 40, "hann", cm256, 0, 60, synth("CF32", 256 * 21 + 9, 0x5EC70203), channel_mode=True)
+    run_case(W, "r2_cs16_n1024_blackman_w16_wf", "CS16", 1024, 16, "blackman", cm256, 6, 30, synth("CS16", 1024 * 16, 0x5EC70204), waterfall=True)
+    run_case(W, "r2_cs8_n64_hamming_w72_wf_split", "CS8", 64, 72, "hamming", cm256, 6, 30, synth("CS8", 64 * 40 + 3, 0x5EC70205), channel_mode=True, waterfall=True)
+
+
 if __name__ == "__main__":
     sys.path.insert(0, os.path.join(ROOT, "spectroplot-js_b200"))
     W = RefWorker()
+    if "--round2-options" in sys.argv:
+        round2_option_cases(W)
+        sys.exit(0)
     if "--large-only" not in sys.argv:
         host_fixtures(W)
         render_cases(W)
