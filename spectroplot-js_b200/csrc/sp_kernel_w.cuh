@@ -37,6 +37,9 @@
 #ifndef SP_W_SEP
 #define SP_W_SEP 1
 #endif
+#ifndef SP_W_SG
+#define SP_W_SG 1
+#endif
 #ifndef SP_W_STSB
 #define SP_W_STSB 1         // exchange stores between the twiddle products (0: in a row after them; the same within noise at N = 512)
 #endif
@@ -45,6 +48,9 @@ namespace sp {
 
 template <int LOG2P, int LOG2T, int FMT> struct WCfg {
     static constexpr int P = 1 << LOG2P, T = 1 << LOG2T, N = P * T, FW = 32 / T, Q = P / T;
+    // T = 8 (N = 64, 128): the bulk copy, its position arithmetic and its barrier serve TWO consecutive warp-steps (8 consecutive frames):
+    // ncu put 22 % of the FFT warps' time of the N = 128 kernel into that per-step bookkeeping
+    static constexpr int SG = (T == 8 && SP_W_SG && SP_W_SEP) ? 2 : 1, FWS = FW * SG;
     static constexpr int NW = P <= 16 ? SP_W_NW16 : SP_W_NW32;                   // FFT warps
     static_assert(NW % 4 == 0, "setmaxnreg is a warpgroup (4 warps) operation: the FFT warps must fill whole warpgroups (a mixed one hangs)");
     static constexpr int FFT_THREADS = 32 * NW, STORE_THREADS = 128, THREADS = FFT_THREADS + STORE_THREADS;
@@ -67,7 +73,7 @@ template <int LOG2P, int LOG2T, int FMT> struct WCfg {
 #if SP_W_SEP
     // the raw frames and the exchange area of a warp do not share bytes: the exchange stores need no "raw frame consumed" fence (they
     // ride between the twiddle products) and the next frames' bulk copy starts as soon as the warp has decoded, not after pass B
-    static constexpr int RAW_BYTES = (FW * RAWP + 15) & ~15;
+    static constexpr int RAW_BYTES = (FWS * RAWP + 15) & ~15;
     static constexpr int XBYTES = RAW_BYTES + ((FW * FSTR * 8 + 15) & ~15);
     static constexpr bool STS_BETWEEN = SP_W_STSB != 0;
 #else
@@ -78,7 +84,7 @@ template <int LOG2P, int LOG2T, int FMT> struct WCfg {
     static constexpr int HALF_WORDS = (N / 4) * FPITCH;
     static constexpr bool TW_SMEM = P > 16 && !SP_W_TWREG32;                     // twiddles from shared memory (31 per thread do not fit 152 registers)
     static constexpr size_t SMEM_BYTES = (size_t)NW * XBYTES + (size_t)2 * HALF_WORDS * 4 + (size_t)JH_SIZE * 4 + (TW_SMEM ? (size_t)T * 32 * 8 : 0)
-                                       + 1024 /* LUT */ + (size_t)F * 8 /* s_mm */ + (size_t)NW * 2 * FW * 4 /* s_off */ + (size_t)NW * 8 + 64
+                                       + 1024 /* LUT */ + (size_t)F * 8 /* s_mm */ + (size_t)NW * 2 * FWS * 4 /* s_off */ + (size_t)NW * 8 + 64
                                        + 128 + 1024 /* LUT alignment */;
 };
 
@@ -111,7 +117,8 @@ template <int LOG2P, int LOG2T, int FMT, bool OPT = false>
 __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_kernel(const Params p, const float2 *__restrict__ twW)
 {
     using B = WCfg<LOG2P, LOG2T, FMT>;
-    constexpr int P = B::P, T = B::T, N = B::N, FW = B::FW, Q = B::Q, NW = B::NW, HF = B::HF, F = B::F;
+    constexpr int P = B::P, T = B::T, N = B::N, FW = B::FW, Q = B::Q, NW = B::NW, HF = B::HF, F = B::F, SG = B::SG, FWS = B::FWS;
+    static_assert(B::WSH % SG == 0, "a stage group must not straddle staging halves");
     constexpr bool FLOAT_IN = FMT == CF32 || FMT == CF64 || FMT == FMT_RUNTIME;   // |X|^2 may be +inf / NaN
     extern __shared__ __align__(128) unsigned char smem_w[];
     const unsigned lut_base = (smem_u32(smem_w) + 1023u) & ~1023u;               // see render_r64_kernel
@@ -148,41 +155,41 @@ __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_
         // lib/worker.js:72) and lane 0 collects them - four positions in the time of one while the warp would otherwise wait for a
         // serial loop in lane 0 (+4 % at N = 128, +3 % at N = 64; with one or two frames per warp the warp-wide double
         // instructions cost more than they save: -2 .. -4 %, so those keep the loop in lane 0)
-        long long p0[FW];
-        if constexpr (FW >= 4) {
-            const int i = lane < FW ? lane : FW - 1;
+        long long p0[FWS];
+        if constexpr (FWS >= 4) {
+            const int i = lane < FWS ? lane : FWS - 1;
             const long long xc = xr + i < p.chunk_frames ? xr + i : p.chunk_frames - 1;   // partial last tile: redo the last frame
             const long long xgl = p.frame_first + p.chunk_first + xc;
             const long long mine = (long long)__dadd_rn(0.5, __dmul_rn(p.stride, (double)xgl)) - p.sample_base;   // lib/worker.js:72
 #pragma unroll
-            for (int k = 0; k < FW; k++) p0[k] = __shfl_sync(0xffffffffu, mine, k);
+            for (int k = 0; k < FWS; k++) p0[k] = __shfl_sync(0xffffffffu, mine, k);
             if (lane != 0) return;
         } else {
             if (lane != 0) return;
 #pragma unroll
-            for (int i = 0; i < FW; i++) {
+            for (int i = 0; i < FWS; i++) {
                 const long long xc = xr + i < p.chunk_frames ? xr + i : p.chunk_frames - 1;
                 const long long xgl = p.frame_first + p.chunk_first + xc;
                 p0[i] = (long long)__dadd_rn(0.5, __dmul_rn(p.stride, (double)xgl)) - p.sample_base;
             }
         }
-        int *off = s_off + (warp * 2 + par) * FW;
+        int *off = s_off + (warp * 2 + par) * FWS;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         // overlapping frames (hop < N): ONE copy of the span, every frame decodes from its own offset in it
-        const long long span = p0[FW - 1] - p0[0] + N;
-        if (FW > 1 && span < (long long)FW * N && span * B::SWB + 32 <= FW * B::RAWP && !(p.dbg & 16)) {     // (SP_DEBUG_SKIP=16: per-frame copies, for the A/B of the reuse counters)
+        const long long span = p0[FWS - 1] - p0[0] + N;
+        if (FWS > 1 && span < (long long)FWS * N && span * B::SWB + 32 <= FWS * B::RAWP && !(p.dbg & 16)) {     // (SP_DEBUG_SKIP=16: per-frame copies, for the A/B of the reuse counters)
             const unsigned long long o0 = (unsigned long long)p0[0] * B::SWB, a0 = o0 & ~15ull;
             const unsigned bytes = (unsigned)(((o0 - a0) + (unsigned long long)span * B::SWB + 15) & ~15ull);
 #pragma unroll
-            for (int i = 0; i < FW; i++) off[i] = (int)((o0 - a0) + (unsigned long long)(p0[i] - p0[0]) * B::SWB);
+            for (int i = 0; i < FWS; i++) off[i] = (int)((o0 - a0) + (unsigned long long)(p0[i] - p0[0]) * B::SWB);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(smem_u32(xs)), "l"(p.buf + a0), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
         } else {
-            unsigned total = 0, bytes[FW];
-            unsigned long long a0[FW];
+            unsigned total = 0, bytes[FWS];
+            unsigned long long a0[FWS];
 #pragma unroll
-            for (int i = 0; i < FW; i++) {
+            for (int i = 0; i < FWS; i++) {
                 const unsigned long long o = (unsigned long long)p0[i] * B::SWB;
                 a0[i] = o & ~15ull;
                 bytes[i] = (unsigned)(((o - a0[i]) + (unsigned long long)N * B::SWB + 15) & ~15ull);
@@ -191,7 +198,7 @@ __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_
             }
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(total) : "memory");
 #pragma unroll
-            for (int i = 0; i < FW; i++)
+            for (int i = 0; i < FWS; i++)
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"(smem_u32(xs + i * B::RAWP)), "l"(p.buf + a0[i]), "r"(bytes[i]), "r"(smem_u32(mbar)) : "memory");
         }
@@ -289,8 +296,8 @@ __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_
 #pragma unroll
         for (int k = 1; k < P; k++) tw[k] = twW[k * T + t];
     }
-    // frames of warp-step (h, j) of a tile: h*HF + (j*NW + warp)*FW .. + FW - 1
-    auto step_first = [&](long long tl, int h, int j) -> long long { return tl * F + h * HF + (j * NW + warp) * FW; };
+    // frames of warp-step (h, j) of a tile: h*HF + ((j/SG)*NW + warp)*FWS + (j%SG)*FW .. + FW - 1 (a warp's SG consecutive steps = FWS consecutive frames)
+    auto step_first = [&](long long tl, int h, int j) -> long long { return tl * F + h * HF + ((j / SG) * NW + warp) * FWS + (j % SG) * FW; };
     if (tile < p.ntiles) stage(step_first(tile, 0, 0), 0);
 
     while (tile < p.ntiles) {
@@ -301,14 +308,15 @@ __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_
             const int j = hj % B::WSH;
             asm volatile("" : "+r"(h));                                 // (see render_r64_kernel: keeps the mbarrier address arithmetic opaque)
             const long long xr = step_first(tile, h, j) + f;            // chunk-relative frame of this thread
-            const int fh = (j * NW + warp) * FW + f;                    // frame within the half
+            const int fh = ((j / SG) * NW + warp) * FWS + (j % SG) * FW + f;   // frame within the half
+            const int r = j % SG;                                       // step within the stage group
             const bool valid = xr < p.chunk_frames;                     // false: past the end of a partial last tile (outputs suppressed)
             const unsigned dump = smem_u32(s_jh + JH_SIZE - 1);         // histogram atomics of such frames land in an unused counter
             cf v[P];
             // ---------------- load + decode + window (lib/worker.js:70-75) ----------------
-            mbar_wait(mbar, fpar);
+            if (r == 0) mbar_wait(mbar, fpar);
             {
-                const unsigned char *rp = xs + s_off[(warp * 2 + fpar) * FW + f];
+                const unsigned char *rp = xs + s_off[(warp * 2 + fpar) * FWS + r * FW + f];
 #pragma unroll
                 for (int a = 0; a < P; a++) v[a] = decode_raw_cf<FMT>(rp, T * a + t, p.format);
                 // raw sample at p0 + n/2 (lib/worker.js:131-133); the power-of-two scale is exact
@@ -316,7 +324,7 @@ __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_
 #pragma unroll
                 for (int a = 0; a < P; a++) v[a] = cscale(v[a], win[a]);
             }
-            fpar ^= 1;
+            if (r == SG - 1) fpar ^= 1;
 
             // ---------------- pass A: DFT-P over the slow input digit, twiddle W_N^{t*k0} ----------------
             dft<P>(v);
@@ -360,7 +368,7 @@ __global__ void __launch_bounds__(WCfg<LOG2P, LOG2T, FMT>::THREADS, 1) render_w_
                 else if (next_tile < p.ntiles) stage(step_first(next_tile, 0, 0), fpar);
             };
 #if SP_W_SEP
-            prefetch();                                                 // the raw area is free: start the bulk copy of the warp's next frames
+            if (r == SG - 1) prefetch();                                // the raw area is free: start the bulk copy of the warp's next frames
 #endif
             // ---------------- pass B: thread u = t owns rows k0 = u + T*q: Q transforms of length T ----------------
 #pragma unroll
