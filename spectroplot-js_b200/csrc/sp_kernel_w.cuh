@@ -40,6 +40,9 @@
 #ifndef SP_W_SG
 #define SP_W_SG 1
 #endif
+#ifndef SP_W_SG_MAXT
+#define SP_W_SG_MAXT 32     // largest T that shares a bulk copy between two warp-steps (A/B: 8 = round-2 build before the last change)
+#endif
 #ifndef SP_W_STSB
 #define SP_W_STSB 1         // exchange stores between the twiddle products (0: in a row after them; the same within noise at N = 512)
 #endif
@@ -48,9 +51,6 @@ namespace sp {
 
 template <int LOG2P, int LOG2T, int FMT> struct WCfg {
     static constexpr int P = 1 << LOG2P, T = 1 << LOG2T, N = P * T, FW = 32 / T, Q = P / T;
-    // T = 8 (N = 64, 128): the bulk copy, its position arithmetic and its barrier serve TWO consecutive warp-steps (8 consecutive frames):
-    // ncu put 22 % of the FFT warps' time of the N = 128 kernel into that per-step bookkeeping
-    static constexpr int SG = (T == 8 && SP_W_SG && SP_W_SEP) ? 2 : 1, FWS = FW * SG;
     static constexpr int NW = P <= 16 ? SP_W_NW16 : SP_W_NW32;                   // FFT warps
     static_assert(NW % 4 == 0, "setmaxnreg is a warpgroup (4 warps) operation: the FFT warps must fill whole warpgroups (a mixed one hangs)");
     static constexpr int FFT_THREADS = 32 * NW, STORE_THREADS = 128, THREADS = FFT_THREADS + STORE_THREADS;
@@ -70,6 +70,16 @@ template <int LOG2P, int LOG2T, int FMT> struct WCfg {
     // (a multiple of 16 bytes: bulk-copy destination)
     static constexpr int RAWP = N * SWB + ((T * SWB >= 128 || T * SWB < 16 || (T * SWB) % 16 != 0) ? 32 : (T * SWB >= 32 ? T * SWB : T * SWB + 128));
     static_assert(RAWP % 16 == 0, "raw slots are bulk-copy destinations");
+    static constexpr int FPITCH = (HF + 31) / 32 * 32 + FW;                      // staging words per word column: STS.32 of a warp conflict-free
+    static constexpr int HALF_WORDS = (N / 4) * FPITCH;
+    static constexpr bool TW_SMEM = P > 16 && !SP_W_TWREG32;                     // twiddles from shared memory (31 per thread do not fit 152 registers)
+    // The bulk copy, its position arithmetic (double) and its barrier serve TWO consecutive warp-steps = 2 FW consecutive frames wherever
+    // the doubled raw area still fits shared memory (every shape for samples of up to 4 bytes): ncu put 22 % of the FFT warps' time of
+    // the N = 128 kernel, and 11 % at N = 512, into that per-step bookkeeping
+    static constexpr size_t SMEM_REST = (size_t)2 * HALF_WORDS * 4 + (size_t)JH_SIZE * 4 + (TW_SMEM ? (size_t)T * 32 * 8 : 0) + 1024 /* LUT */
+                                      + (size_t)F * 8 /* s_mm */ + (size_t)NW * 8 + 64 + 128 + 1024 /* LUT alignment */;
+    static constexpr size_t SMEM_SG2 = (size_t)NW * (((2 * FW * RAWP + 15) & ~15) + ((FW * FSTR * 8 + 15) & ~15)) + (size_t)NW * 2 * 2 * FW * 4 + SMEM_REST;
+    static constexpr int SG = (SP_W_SG && SP_W_SEP && T <= SP_W_SG_MAXT && WSH % 2 == 0 && SMEM_SG2 <= 232448) ? 2 : 1, FWS = FW * SG;
 #if SP_W_SEP
     // the raw frames and the exchange area of a warp do not share bytes: the exchange stores need no "raw frame consumed" fence (they
     // ride between the twiddle products) and the next frames' bulk copy starts as soon as the warp has decoded, not after pass B
@@ -80,12 +90,7 @@ template <int LOG2P, int LOG2T, int FMT> struct WCfg {
     static constexpr int RAW_BYTES = 0;
     static constexpr int XBYTES = ((FW * FSTR * 8 > FW * RAWP ? FW * FSTR * 8 : FW * RAWP) + 15) & ~15;
 #endif
-    static constexpr int FPITCH = (HF + 31) / 32 * 32 + FW;                      // staging words per word column: STS.32 of a warp conflict-free
-    static constexpr int HALF_WORDS = (N / 4) * FPITCH;
-    static constexpr bool TW_SMEM = P > 16 && !SP_W_TWREG32;                     // twiddles from shared memory (31 per thread do not fit 152 registers)
-    static constexpr size_t SMEM_BYTES = (size_t)NW * XBYTES + (size_t)2 * HALF_WORDS * 4 + (size_t)JH_SIZE * 4 + (TW_SMEM ? (size_t)T * 32 * 8 : 0)
-                                       + 1024 /* LUT */ + (size_t)F * 8 /* s_mm */ + (size_t)NW * 2 * FWS * 4 /* s_off */ + (size_t)NW * 8 + 64
-                                       + 128 + 1024 /* LUT alignment */;
+    static constexpr size_t SMEM_BYTES = (size_t)NW * XBYTES + (size_t)NW * 2 * FWS * 4 /* s_off */ + SMEM_REST;
 };
 
 // min / max over the T lanes of a frame (aligned groups of T lanes).  A __reduce_*_sync with a partial mask makes the warp's
