@@ -80,3 +80,30 @@ def test_shard_plan_covers_every_frame_once():
             assert s["sample_first"] <= p_first and s["sample_first"] + s["sample_count"] >= p_last
             assert s["sample_first"] % 4 == 0                     # 16-byte alignment for <= 4-byte... samples
             assert s["sample_first"] + s["sample_count"] <= total_samples
+
+
+def test_cu8_two_instruction_division_is_correctly_rounded():
+    """csrc/sp_device.cuh decodes cu8 as x / 255 = fma(x, r_hi, x * r_lo) with 1/255 split into two fp32 constants (one packed
+    instruction less than the Markstein form).  The claim that this is the correctly rounded quotient - i.e. fround((c - 127.5) /
+    127.5) of lib/samples.js:313-330 - for every code is checked here exactly, with the constants read from the source."""
+    import os
+    import re
+    from fractions import Fraction
+    src = open(os.path.join(os.path.dirname(__file__), "..", "spectroplot-js_b200", "csrc", "sp_device.cuh")).read()
+    m = re.search(r"r_hi = ([0-9.eE+-]+)f, r_lo = ([0-9.eE+-]+)f", src)
+    assert m, "constants not found"
+    r_hi, r_lo = np.float32(m.group(1)), np.float32(m.group(2))
+    assert r_hi == np.float32(1.0 / 255.0) and r_lo == np.float32(1.0 / 255.0 - float(r_hi))
+
+    def rn32(fr):                                   # correctly rounded fp32 of an exact rational (no double rounding)
+        lo, hi = np.float32(float(fr)), None
+        cands = {lo, np.nextafter(lo, np.float32(np.inf)), np.nextafter(lo, np.float32(-np.inf))}
+        best = min(cands, key=lambda v: (abs(Fraction(float(v)) - fr), int(np.float32(v).view(np.uint32)) & 1))
+        return np.float32(best)
+
+    for c in range(256):
+        x = np.float32(2 * c - 255)
+        lo = np.float32(x * r_lo)                                                  # FMUL2
+        q = rn32(Fraction(float(x)) * Fraction(float(r_hi)) + Fraction(float(lo)))  # FFMA2: one rounding of the exact sum
+        ref = np.float32((c - 127.5) / 127.5)                                      # Math.fround of the reference's double value
+        assert q == ref, (c, float(q), float(ref))
